@@ -1,0 +1,435 @@
+/*
+ * nbldpc_host.c -- host side of the B200 EMS NB-LDPC decoder, plain C (no CUDA).
+ *
+ * What the reference does once per run on the CPU stays on the CPU here, behind the same meaning:
+ *   alist parsing            LoadCode            init.c:143-272   (both dialects, runtime switch)
+ *   GF(q) tables             LoadTables          init.c:427-506   (+ Table_Add/Mul/Div_GF 37-130)
+ *   systematic encoder       GaussianElimination tools.c:151-218, Encoding tools.c:232-268
+ *   frame source / noise     RandomBinaryGenerator tools.c:124, ModelChannel_AWGN_BPSK channel.c:51-62
+ *   statistics               NB_LDPC.c:474-507
+ * plus what only the GPU path needs: the conflict-free step schedule of one decoding pass.
+ */
+#include "nbldpc_internal.h"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static __thread char g_err[512];
+
+void nbgpu_set_global_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+const char *nbgpu_get_global_error(void) { return g_err; }
+
+const char *nbgpu_version(void) { return "nbldpc_b200 0.1 (sm_100a)"; }
+
+/* ------------------------------------------------------------------------------------------------
+ * GF(2^m): symbol 0 is zero, symbol k is alpha^(k-1) (struct.h:119-476 are the binary images for the
+ * primitive polynomials x^4+x+1, x^6+x+1, x^8+x^4+x^3+x^2+1 with bit l = coefficient of x^l).
+ * ---------------------------------------------------------------------------------------------- */
+static int field_poly(int q)
+{
+    switch (q) { case 16: return 0x13; case 64: return 0x43; case 256: return 0x11D; default: return 0; }
+}
+
+static int make_tables(struct nbgpu_code *c, const int *bingf, const int *addgf, const int *mulgf, const int *divgf)
+{
+    const int q = c->q, lg = c->logq;
+    int a, b, l;
+    c->bingf = malloc(sizeof(int) * q * lg);
+    c->addgf = malloc(sizeof(int) * q * q);
+    c->mulgf = malloc(sizeof(int) * q * q);
+    c->divgf = malloc(sizeof(int) * q * q);
+    c->img = malloc(sizeof(int) * q);
+    c->inv = malloc(sizeof(int) * q);
+    if (!c->bingf || !c->addgf || !c->mulgf || !c->divgf || !c->img || !c->inv) return NBGPU_ENOMEM;
+    if (bingf) {
+        memcpy(c->bingf, bingf, sizeof(int) * q * lg);
+    } else {
+        int poly = field_poly(q), x = 1, k;
+        if (!poly) { nbgpu_set_global_error("GF(%d) is not supported (16, 64, 256 only, as init.c:431)", q); return NBGPU_EINVAL; }
+        for (l = 0; l < lg; l++) c->bingf[l] = 0;
+        for (k = 1; k < q; k++) {
+            for (l = 0; l < lg; l++) c->bingf[k * lg + l] = (x >> l) & 1;
+            x <<= 1;
+            if (x & q) x ^= poly;
+        }
+    }
+    for (a = 0; a < q; a++) c->inv[a] = -1;
+    for (a = 0; a < q; a++) {
+        int v = 0;
+        for (l = 0; l < lg; l++) v |= (c->bingf[a * lg + l] & 1) << l;
+        c->img[a] = v;
+        if (c->inv[v] != -1) { nbgpu_set_global_error("BINGF is not a bijection (symbols %d and %d)", c->inv[v], a); return NBGPU_EINVAL; }
+        c->inv[v] = a;
+    }
+    if (addgf) memcpy(c->addgf, addgf, sizeof(int) * q * q);
+    else for (a = 0; a < q; a++) for (b = 0; b < q; b++) c->addgf[a * q + b] = c->inv[c->img[a] ^ c->img[b]];
+    if (mulgf) memcpy(c->mulgf, mulgf, sizeof(int) * q * q);
+    else for (a = 0; a < q; a++) for (b = 0; b < q; b++)
+        c->mulgf[a * q + b] = (a && b) ? ((a + b - 2) % (q - 1)) + 1 : 0;
+    if (divgf) memcpy(c->divgf, divgf, sizeof(int) * q * q);
+    else for (a = 0; a < q; a++) for (b = 0; b < q; b++)
+        c->divgf[a * q + b] = (b == 0) ? -1 : (a ? ((a - b + (q - 1)) % (q - 1)) + 1 : 0);
+    /* The kernels work on binary images (GF addition == XOR).  Check that whatever tables we were
+     * handed really have that structure, and that MUL/DIV are consistent. */
+    for (a = 0; a < q; a++) for (b = 0; b < q; b++) {
+        if (c->addgf[a * q + b] != c->inv[c->img[a] ^ c->img[b]]) {
+            nbgpu_set_global_error("ADDGF[%d][%d] is not the XOR of the binary images", a, b); return NBGPU_EINVAL;
+        }
+        int m = c->mulgf[a * q + b];
+        if (m < 0 || m >= q || m != c->mulgf[b * q + a]) { nbgpu_set_global_error("MULGF[%d][%d] invalid", a, b); return NBGPU_EINVAL; }
+        if (b != 0 && c->divgf[m * q + b] != a && !(a == 0 && c->divgf[m * q + b] == 0)) {
+            nbgpu_set_global_error("DIVGF is not the inverse of MULGF at (%d,%d)", a, b); return NBGPU_EINVAL;
+        }
+    }
+    return NBGPU_OK;
+}
+
+static void finish_graph(struct nbgpu_code *c)
+{
+    int m;
+    c->row_ptr = malloc(sizeof(int) * (c->M + 1));
+    c->row_ptr[0] = 0;
+    c->dc_max = 0; c->dc_min = 1 << 30;
+    for (m = 0; m < c->M; m++) {
+        c->row_ptr[m + 1] = c->row_ptr[m] + c->row_deg[m];
+        if (c->row_deg[m] > c->dc_max) c->dc_max = c->row_deg[m];
+        if (c->row_deg[m] < c->dc_min) c->dc_min = c->row_deg[m];
+    }
+}
+
+static int check_graph(const struct nbgpu_code *c)
+{
+    int e;
+    for (e = 0; e < c->E; e++) {
+        if (c->col[e] < 0 || c->col[e] >= c->N) { nbgpu_set_global_error("edge %d: column %d out of range", e, c->col[e]); return NBGPU_EINVAL; }
+        if (c->val[e] < 1 || c->val[e] >= c->q) { nbgpu_set_global_error("edge %d: coefficient %d out of range", e, c->val[e]); return NBGPU_EINVAL; }
+    }
+    return NBGPU_OK;
+}
+
+int nbgpu_code_load(nbgpu_code **out, const char *path, int dialect)
+{
+    *out = NULL;
+    FILE *f = fopen(path, "r");
+    if (!f) { nbgpu_set_global_error("cannot open matrix file '%s'", path); return NBGPU_EIO; }
+    struct nbgpu_code *c = calloc(1, sizeof *c);
+    int rc = NBGPU_EIO, n, m, k;
+    int *coldeg = NULL, *rest = NULL;
+    if (fscanf(f, "%d %d %d", &c->N, &c->M, &c->q) != 3 || c->N <= 0 || c->M <= 0 || c->M > c->N) {
+        nbgpu_set_global_error("'%s': bad alist header", path); goto fail;
+    }
+    c->logq = (int)rint(log((double)c->q) / log(2.0));                 /* init.c:160-163 */
+    if ((1 << c->logq) != c->q || !field_poly(c->q)) {
+        nbgpu_set_global_error("GF(%d) is not supported (16, 64, 256 only, as init.c:431)", c->q); rc = NBGPU_EINVAL; goto fail;
+    }
+    c->K = c->N - c->M;
+    c->rate = (float)(c->N - c->M) / c->N;                             /* init.c:167 */
+    coldeg = malloc(sizeof(int) * c->N);
+    for (n = 0; n < c->N; n++) if (fscanf(f, "%d", &coldeg[n]) != 1) { nbgpu_set_global_error("'%s': truncated column degrees", path); goto fail; }
+    c->row_deg = malloc(sizeof(int) * c->M);
+    for (m = 0; m < c->M; m++) if (fscanf(f, "%d", &c->row_deg[m]) != 1 || c->row_deg[m] < 0) { nbgpu_set_global_error("'%s': truncated row degrees", path); goto fail; }
+    finish_graph(c);
+    c->E = c->row_ptr[c->M];
+    rest = malloc(sizeof(int) * 2 * (size_t)c->E);
+    for (k = 0; k < 2 * c->E; k++) if (fscanf(f, "%d", &rest[k]) != 1) { nbgpu_set_global_error("'%s': truncated edge list (%d of %d values)", path, k, 2 * c->E); goto fail; }
+    if (dialect == NBGPU_ALIST_AUTO) {
+        /* a dialect is plausible when all values are in range and the column degrees of the header are met */
+        int ok_ubs = 1, ok_kn = 1;
+        int *cnt = calloc(c->N, sizeof(int));
+        for (k = 0; k < c->E && ok_ubs; k++) {
+            if (rest[k] < 0 || rest[k] >= c->N || rest[c->E + k] < 1 || rest[c->E + k] >= c->q) ok_ubs = 0; else cnt[rest[k]]++;
+        }
+        for (n = 0; n < c->N && ok_ubs; n++) if (cnt[n] != coldeg[n]) ok_ubs = 0;
+        memset(cnt, 0, sizeof(int) * c->N);
+        for (k = 0; k < c->E && ok_kn; k++) {
+            if (rest[2 * k] < 1 || rest[2 * k] > c->N || rest[2 * k + 1] < 0 || rest[2 * k + 1] > c->q - 2) ok_kn = 0; else cnt[rest[2 * k] - 1]++;
+        }
+        for (n = 0; n < c->N && ok_kn; n++) if (cnt[n] != coldeg[n]) ok_kn = 0;
+        free(cnt);
+        if (ok_ubs == ok_kn) {
+            nbgpu_set_global_error("'%s': cannot tell the alist dialect (%s); pass NBGPU_ALIST_UBS or NBGPU_ALIST_KN",
+                                   path, ok_ubs ? "both fit" : "neither fits");
+            rc = NBGPU_EINVAL; goto fail;
+        }
+        dialect = ok_ubs ? NBGPU_ALIST_UBS : NBGPU_ALIST_KN;
+    }
+    c->dialect = dialect;
+    c->col = malloc(sizeof(int) * c->E);
+    c->val = malloc(sizeof(int) * c->E);
+    for (k = 0; k < c->E; k++) {
+        if (dialect == NBGPU_ALIST_KN) { c->col[k] = rest[2 * k] - 1; c->val[k] = rest[2 * k + 1] + 1; }   /* init.c:218-221 */
+        else { c->col[k] = rest[k]; c->val[k] = rest[c->E + k]; }                                          /* init.c:197-205 */
+    }
+    if ((rc = check_graph(c)) != NBGPU_OK) goto fail;
+    if ((rc = make_tables(c, NULL, NULL, NULL, NULL)) != NBGPU_OK) goto fail;
+    free(coldeg); free(rest); fclose(f);
+    *out = c;
+    return NBGPU_OK;
+fail:
+    free(coldeg); free(rest); fclose(f);
+    nbgpu_code_free(c);
+    return rc;
+}
+
+int nbgpu_code_from_arrays(nbgpu_code **out, int N, int M, int q, const int *row_deg, const int *col,
+                           const int *val, const int *bingf, const int *addgf, const int *mulgf, const int *divgf)
+{
+    *out = NULL;
+    if (N <= 0 || M <= 0 || M > N || !row_deg || !col || !val) { nbgpu_set_global_error("bad code arrays"); return NBGPU_EINVAL; }
+    struct nbgpu_code *c = calloc(1, sizeof *c);
+    int rc;
+    c->N = N; c->M = M; c->K = N - M; c->q = q;
+    c->logq = (int)rint(log((double)q) / log(2.0));
+    if ((1 << c->logq) != q || q < 4 || q > 256 || (!bingf && !field_poly(q))) {
+        nbgpu_set_global_error("GF(%d) is not supported", q); free(c); return NBGPU_EINVAL;
+    }
+    c->rate = (float)(N - M) / N;
+    c->row_deg = malloc(sizeof(int) * M);
+    memcpy(c->row_deg, row_deg, sizeof(int) * M);
+    finish_graph(c);
+    c->E = c->row_ptr[M];
+    c->col = malloc(sizeof(int) * c->E); c->val = malloc(sizeof(int) * c->E);
+    memcpy(c->col, col, sizeof(int) * c->E); memcpy(c->val, val, sizeof(int) * c->E);
+    c->dialect = 0;
+    if ((rc = check_graph(c)) != NBGPU_OK || (rc = make_tables(c, bingf, addgf, mulgf, divgf)) != NBGPU_OK) { nbgpu_code_free(c); return rc; }
+    *out = c;
+    return NBGPU_OK;
+}
+
+void nbgpu_code_free(nbgpu_code *c)
+{
+    if (!c) return;
+    free(c->row_deg); free(c->row_ptr); free(c->col); free(c->val);
+    free(c->bingf); free(c->addgf); free(c->mulgf); free(c->divgf); free(c->img); free(c->inv);
+    free(c->piv_col); free(c->perm); free(c->ut_ptr); free(c->ut_col); free(c->ut_val);
+    free(c);
+}
+
+void nbgpu_code_info(const nbgpu_code *c, int *info)
+{
+    info[0] = c->N; info[1] = c->M; info[2] = c->K; info[3] = c->q; info[4] = c->logq; info[5] = c->E;
+    info[6] = c->dc_max; info[7] = c->dc_min; info[8] = c->dialect; info[9] = 0;
+}
+float nbgpu_code_rate(const nbgpu_code *c) { return c->rate; }
+void nbgpu_code_graph(const nbgpu_code *c, int *row_deg, int *col, int *val)
+{
+    if (row_deg) memcpy(row_deg, c->row_deg, sizeof(int) * c->M);
+    if (col) memcpy(col, c->col, sizeof(int) * c->E);
+    if (val) memcpy(val, c->val, sizeof(int) * c->E);
+}
+void nbgpu_code_tables(const nbgpu_code *c, int *bingf, int *addgf, int *mulgf, int *divgf)
+{
+    if (bingf) memcpy(bingf, c->bingf, sizeof(int) * c->q * c->logq);
+    if (addgf) memcpy(addgf, c->addgf, sizeof(int) * c->q * c->q);
+    if (mulgf) memcpy(mulgf, c->mulgf, sizeof(int) * c->q * c->q);
+    if (divgf) memcpy(divgf, c->divgf, sizeof(int) * c->q * c->q);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * drand48 recurrence (glibc): X <- (0x5DEECE66D X + 0xB) mod 2^48, value X / 2^48.
+ * ---------------------------------------------------------------------------------------------- */
+#define RNG_A 0x5DEECE66DULL
+#define RNG_C 0xBULL
+#define RNG_M ((1ULL << 48) - 1)
+void nbgpu_rng_reference_default(nbgpu_rng *r) { r->x = 0; }
+double nbgpu_rng_drand48(nbgpu_rng *r)
+{
+    r->x = (RNG_A * r->x + RNG_C) & RNG_M;
+    return (double)r->x * (1.0 / 281474976710656.0);
+}
+void nbgpu_rng_skip(nbgpu_rng *r, uint64_t n)
+{
+    uint64_t mul = RNG_A, add = RNG_C, accm = 1, acca = 0;
+    for (; n; n >>= 1) {
+        if (n & 1) { accm = (accm * mul) & RNG_M; acca = (acca * mul + add) & RNG_M; }
+        add = ((mul + 1) * add) & RNG_M;
+        mul = (mul * mul) & RNG_M;
+    }
+    r->x = (accm * r->x + acca) & RNG_M;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder.  Same elimination order, pivot choice and column swaps as tools.c:151-218 so that the
+ * codeword of a given information word is the reference's; the triangular matrix is kept sparse.
+ * ---------------------------------------------------------------------------------------------- */
+int nbgpu_code_prepare_encoder(nbgpu_code *c)
+{
+    if (c->enc_ready) return NBGPU_OK;
+    const int N = c->N, M = c->M, q = c->q;
+    unsigned char *U = calloc((size_t)M * N, 1);
+    int *perm = malloc(sizeof(int) * N);
+    if (!U || !perm) { free(U); free(perm); nbgpu_set_global_error("out of memory in encoder setup"); return NBGPU_ENOMEM; }
+    int m, n, k, r;
+    for (n = 0; n < N; n++) perm[n] = n;
+    for (m = 0; m < M; m++) for (k = c->row_ptr[m]; k < c->row_ptr[m + 1]; k++) U[(size_t)m * N + c->col[k]] = (unsigned char)c->val[k];
+    for (m = 0; m < M; m++) {
+        unsigned char *pr = U + (size_t)m * N;
+        int ind = m;
+        while (ind < N && pr[ind] == 0) ind++;
+        if (ind == N) { free(U); free(perm); nbgpu_set_global_error("The matrix is not full rank (%d,%d)", m, ind); return NBGPU_ERANK; }
+        if (ind != m) {
+            int t = perm[ind]; perm[ind] = perm[m]; perm[m] = t;
+            for (r = 0; r < M; r++) { unsigned char *x = U + (size_t)r * N; unsigned char u = x[m]; x[m] = x[ind]; x[ind] = u; }
+        }
+        const int piv = pr[m];
+        for (r = m + 1; r < M; r++) {
+            unsigned char *x = U + (size_t)r * N;
+            const int lead = x[m];
+            if (!lead) continue;
+            for (n = m; n < N; n++) {
+                int v = x[n];
+                if (v) v = c->divgf[v * q + lead];
+                if (v) v = c->mulgf[v * q + piv];
+                x[n] = (unsigned char)c->addgf[v * q + pr[n]];
+            }
+        }
+    }
+    size_t nnz = 0;
+    for (m = 0; m < M; m++) for (n = m; n < N; n++) nnz += U[(size_t)m * N + n] != 0;
+    c->ut_ptr = malloc(sizeof(int) * (M + 1));
+    c->ut_col = malloc(sizeof(int) * nnz);
+    c->ut_val = malloc(sizeof(int) * nnz);
+    c->piv_col = malloc(sizeof(int) * M);
+    nnz = 0;
+    for (m = 0; m < M; m++) {
+        c->ut_ptr[m] = (int)nnz;
+        c->piv_col[m] = U[(size_t)m * N + m];
+        for (n = m + 1; n < N; n++) if (U[(size_t)m * N + n]) { c->ut_col[nnz] = n; c->ut_val[nnz] = U[(size_t)m * N + n]; nnz++; }
+    }
+    c->ut_ptr[M] = (int)nnz;
+    c->perm = perm;
+    free(U);
+    c->enc_ready = 1;
+    return NBGPU_OK;
+}
+
+static float draw_float(nbgpu_rng *r) { return (float)nbgpu_rng_drand48(r); }      /* My_drand48, tools.c:73 */
+
+int nbgpu_random_codeword(const nbgpu_code *c, nbgpu_rng *r, int *codeword, int *nbin)
+{
+    if (!c->enc_ready) { nbgpu_set_global_error("call nbgpu_code_prepare_encoder first"); return NBGPU_EINVAL; }
+    const int N = c->N, M = c->M, q = c->q, lg = c->logq;
+    int *ns = malloc(sizeof(int) * N);
+    int k, l, m, n;
+    for (k = 0; k < c->K; k++) {                       /* tools.c:129-135: bit = floor(u * 1.9999) */
+        int bits = 0;
+        for (l = 0; l < lg; l++) bits |= ((int)floor(draw_float(r) * 1.9999)) << l;
+        ns[M + k] = c->inv[bits];
+    }
+    for (m = M - 1; m >= 0; m--) {                     /* tools.c:244-254 */
+        int acc = 0;
+        for (k = c->ut_ptr[m]; k < c->ut_ptr[m + 1]; k++)
+            acc = c->addgf[acc * q + c->mulgf[c->ut_val[k] * q + ns[c->ut_col[k]]]];
+        ns[m] = c->divgf[acc * q + c->piv_col[m]];
+    }
+    for (n = 0; n < N; n++) codeword[c->perm[n]] = ns[n];                             /* tools.c:257-258 */
+    if (nbin) for (n = 0; n < N; n++) for (l = 0; l < lg; l++) nbin[n * lg + l] = c->bingf[codeword[n] * lg + l];
+    free(ns);
+    return NBGPU_OK;
+}
+
+float nbgpu_sigma(const nbgpu_code *c, float EbN)
+{
+    return (float)sqrt(1.0 / (2.0 * c->rate * pow(10, EbN / 10.0)));                    /* channel.c:51 */
+}
+
+int nbgpu_awgn_bpsk_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin, float EbN, float *noisy)
+{
+    const double pi = 3.1415926536;                                                     /* channel.c:18 */
+    const float sigma = nbgpu_sigma(c, EbN);
+    const int cnt = c->N * c->logq;
+    int i;
+    for (i = 0; i < cnt; i++) {
+        float u = draw_float(r);
+        float v = draw_float(r);
+        int s = 1 - 2 * (nbin ? nbin[i] : 0);
+        noisy[i] = (float)(s + sigma * sqrt(-2.0 * log(u)) * cos(2.0 * pi * v));          /* channel.c:59 */
+    }
+    return NBGPU_OK;
+}
+
+/* NB_LDPC.c:474-507 */
+int nbgpu_accumulate_stats(const nbgpu_code *c, const int *codeword_bits, const int *decide,
+                           const int *synd, const int *iters, int B, long *stats)
+{
+    const int N = c->N, lg = c->logq;
+    int f, k, l;
+    for (f = 0; f < B; f++) {
+        if (stats[5]) break;
+        int e = 0;
+        const int *d = decide + (size_t)f * N;
+        const int *cb = codeword_bits + (size_t)f * N * lg;
+        for (k = 0; k < c->K; k++) {
+            if (d[k] < 0 || d[k] >= c->q) { nbgpu_set_global_error("decision out of range"); return NBGPU_EINVAL; }
+            for (l = 0; l < lg; l++) e += c->bingf[d[k] * lg + l] != cb[k * lg + l];
+        }
+        stats[0] += 1;
+        stats[4] += iters[f];
+        stats[3] += e;
+        if (e) { stats[1] += 1; if (synd[f] == 0) stats[2] += 1; }
+        if (stats[1] == 40) stats[5] = 1;
+    }
+    return NBGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Pass schedule.  The reference updates check nodes 0..M-1 in file order and rewrites APP after
+ * each one (NB_LDPC.c:320, 448), so node m must see the APP rows written by every earlier node that
+ * shares a variable with it -- and nothing else constrains the order.  Nodes are packed first-fit
+ * into steps of at most 'cap' mutually independent nodes: step(m) > step(m') for every earlier m'
+ * that shares a variable.  Any such packing reproduces the reference bit for bit.
+ * ---------------------------------------------------------------------------------------------- */
+int nbgpu_build_schedule(const struct nbgpu_code *c, int cap, nbgpu_schedule *out)
+{
+    const int M = c->M, N = c->N;
+    int m, k;
+    int *last_step = malloc(sizeof(int) * N);     /* step of the latest node (file order) touching a variable */
+    int *step_of = malloc(sizeof(int) * M);
+    int *fill = calloc((size_t)M + 1, sizeof(int));
+    int *first_free = malloc(sizeof(int));
+    int nsteps = 0, depth = 0;
+    int *lvl_var = malloc(sizeof(int) * N);
+    if (cap < 1) cap = 1;
+    for (k = 0; k < N; k++) { last_step[k] = -1; lvl_var[k] = -1; }
+    *first_free = 0;
+    for (m = 0; m < M; m++) {
+        int s = 0, lv = 0;
+        for (k = c->row_ptr[m]; k < c->row_ptr[m + 1]; k++) {
+            if (last_step[c->col[k]] + 1 > s) s = last_step[c->col[k]] + 1;
+            if (lvl_var[c->col[k]] + 1 > lv) lv = lvl_var[c->col[k]] + 1;
+        }
+        if (s < *first_free) s = *first_free;
+        while (fill[s] >= cap) s++;
+        fill[s]++;
+        while (*first_free < M && fill[*first_free] >= cap) (*first_free)++;
+        step_of[m] = s;
+        if (s + 1 > nsteps) nsteps = s + 1;
+        if (lv + 1 > depth) depth = lv + 1;
+        for (k = c->row_ptr[m]; k < c->row_ptr[m + 1]; k++) { last_step[c->col[k]] = s; lvl_var[c->col[k]] = lv; }
+    }
+    out->nsteps = nsteps;
+    out->depth = depth;
+    out->step_ptr = calloc((size_t)nsteps + 1, sizeof(int));
+    out->order = malloc(sizeof(int) * M);
+    for (m = 0; m < M; m++) out->step_ptr[step_of[m] + 1]++;
+    for (k = 0; k < nsteps; k++) out->step_ptr[k + 1] += out->step_ptr[k];
+    int *pos = malloc(sizeof(int) * (nsteps + 1));
+    memcpy(pos, out->step_ptr, sizeof(int) * (nsteps + 1));
+    for (m = 0; m < M; m++) out->order[pos[step_of[m]]++] = m;      /* file order inside a step */
+    free(pos); free(last_step); free(step_of); free(fill); free(first_free); free(lvl_var);
+    return NBGPU_OK;
+}
+
+void nbgpu_free_schedule(nbgpu_schedule *s)
+{
+    free(s->step_ptr); free(s->order);
+    s->step_ptr = NULL; s->order = NULL; s->nsteps = 0;
+}
