@@ -1,0 +1,188 @@
+"""Host side of the product (plain C, no GPU needed): alist loader, GF tables, frame source, statistics,
+pass schedule, and the C-ABI surface itself."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import nbldpc
+import oracle_lib as ol
+from common import Golden, golden_names, matrix_path, oracle_frames, product_frames, random_regular_code, write_alist_ubs, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nbldpc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(nbgpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    L = C.CDLL(nbldpc.LIB_PATH)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", nbldpc.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (nbgpu_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_no_gpu_means_error_not_fallback():
+    if nbldpc.device_count() > 0:
+        pytest.skip("a GPU is present")
+    code = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
+    with pytest.raises(nbldpc.NbgpuError) as e:
+        nbldpc.Decoder(code, 20, 25, 10, 0.3)
+    assert e.value.code == nbldpc.ECUDA and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("rel,dialect", [("matrices/N96_K48_GF64", 1), ("matrices/KN/N96_K48_GF64.txt", 2),
+                                         ("matrices/KN/N96_K48_GF256.txt", 2), ("matrices/Ahmed_64800_R34_GF16", 1),
+                                         ("matrices/AD_64800_R12_GF256", 1), ("matrices/MatDeclercq_R12_GF64", 1),
+                                         ("matrices/KN/N576_K480_GF64.txt", 2), ("matrices/Mat212_N480_M80", 1)])
+def test_loader_and_tables_equal_oracle(rel, dialect):
+    p = matrix_path(rel)
+    o = ol.Oracle(p, dialect)
+    for d in (dialect, nbldpc.ALIST_AUTO):
+        c = nbldpc.Code(p, d)
+        assert c.dialect == dialect
+        assert (c.N, c.M, c.K, c.q, c.logq, c.E, c.dc_max) == (o.N, o.M, o.K, o.GF, o.logGF, o.E, o.dc_max)
+        assert np.float32(c.rate) == np.float32(o.rate)
+        assert (c.row_deg == o.row_deg).all() and (c.col == o.col).all() and (c.val == o.val).all()
+        b, a, m, dv = c.tables()
+        assert (b == o.bingf).all() and (a == o.addgf).all() and (m == o.mulgf).all() and (dv == o.divgf).all()
+        c.close()
+    o.close()
+
+
+def test_same_code_in_both_dialects():
+    a = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
+    b = nbldpc.Code(matrix_path("matrices/KN/N96_K48_GF64.txt"))
+    assert a.dialect == 1 and b.dialect == 2
+    assert (a.col == b.col).all() and (a.val == b.val).all()
+
+
+def test_loader_errors(tmp_path):
+    with pytest.raises(nbldpc.NbgpuError) as e:
+        nbldpc.Code(str(tmp_path / "missing"))
+    assert e.value.code == nbldpc.EIO
+    p = tmp_path / "bad_gf"
+    p.write_text("4 2 32\n1 1 1 1\n2 2\n0 1\n2 3\n1 1\n1 1\n")
+    with pytest.raises(nbldpc.NbgpuError) as e:
+        nbldpc.Code(str(p))
+    assert e.value.code == nbldpc.EINVAL                       # init.c:431-435 exits; we return an error
+    p = tmp_path / "short"
+    p.write_text("4 2 16\n1 1 1 1\n2 2\n0 1\n2\n")
+    with pytest.raises(nbldpc.NbgpuError) as e:
+        nbldpc.Code(str(p))
+    assert e.value.code == nbldpc.EIO
+    rng = np.random.default_rng(0)
+    a = random_regular_code(rng, 12, 6, 16, 4)
+    a["col"][3] = 99
+    with pytest.raises(nbldpc.NbgpuError):
+        nbldpc.Code(arrays=a)
+
+
+def test_from_arrays_roundtrip(tmp_path):
+    rng = np.random.default_rng(5)
+    a = random_regular_code(rng, 24, 12, 64, 4)
+    c1 = nbldpc.Code(arrays=a)
+    write_alist_ubs(str(tmp_path / "m"), a)
+    c2 = nbldpc.Code(str(tmp_path / "m"))
+    assert c2.dialect == 1 and (c1.col == c2.col).all() and (c1.val == c2.val).all()
+    o = ol.Oracle(str(tmp_path / "m"))
+    b, ad, m, dv = c1.tables()
+    assert (ad == o.addgf).all() and (m == o.mulgf).all() and (dv == o.divgf).all()
+    # reference tables handed in explicitly (the INTEGRATION.md route) are accepted, broken ones are not
+    a2 = dict(a, bingf=o.bingf, addgf=o.addgf, mulgf=o.mulgf, divgf=o.divgf)
+    nbldpc.Code(arrays=a2).close()
+    bad = o.addgf.copy(); bad[3, 5] ^= 1
+    with pytest.raises(nbldpc.NbgpuError):
+        nbldpc.Code(arrays=dict(a2, addgf=bad))
+
+
+@pytest.mark.parametrize("name", ["n96_gf64_nm20", "n96_gf256_kn_nm20", "mat24_n480_nm16", "mat28_n72_nm12", "ahmed_r34_gf16_nm16"])
+def test_frame_source_equals_reference_stream(name):
+    g = Golden(name)
+    c = nbldpc.Code(matrix_path(g.matrix))
+    o = ol.Oracle(matrix_path(g.matrix), g.dialect)
+    nf = min(g.nf, 3)
+    pf, sigma = product_frames(c, nf, g.ebn)
+    of, osig = oracle_frames(o, nf, g.ebn, want_llr=False)
+    assert np.float32(sigma) == np.float32(osig)
+    for f in range(nf):
+        assert (pf[f]["nbin"] == g.z["nbin"][f]).all()
+        assert (pf[f]["cw"] == of[f]["cw"]).all()
+        assert pf[f]["noisy"].tobytes() == of[f]["noisy"].tobytes()
+        assert o.syndrome(pf[f]["cw"]) == 0
+    o.close()
+
+
+def test_rng_jump_ahead_gives_independent_frames():
+    c = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
+    c.prepare_encoder()
+    pf, _ = product_frames(c, 4, 3.0)
+    D = (c.K + 2 * c.N) * c.logq                      # drand48 draws per frame
+    c.rng_default(); c.rng_skip(3 * D)
+    cw, nbin = c.random_codeword()
+    assert (cw == pf[3]["cw"]).all()
+    assert c.noise(nbin, 3.0).tobytes() == pf[3]["noisy"].tobytes()
+
+
+def test_rank_deficient_matrix_is_an_error():
+    a = dict(N=4, M=2, q=16, row_deg=np.array([2, 2], np.int32), col=np.array([0, 1, 0, 1], np.int32),
+             val=np.array([1, 1, 1, 1], np.int32))
+    c = nbldpc.Code(arrays=a)
+    with pytest.raises(nbldpc.NbgpuError) as e:
+        c.prepare_encoder()
+    assert e.value.code == nbldpc.ERANK                 # tools.c:181-185 exits
+
+
+def test_statistics_follow_reference_rules():
+    """NB_LDPC.c:474-507 incl. the stop at the 40th erroneous frame, against the oracle's Monte-Carlo loop."""
+    p = matrix_path("matrices/N96_K48_GF64")
+    o = ol.Oracle(p)
+    c = nbldpc.Code(p)
+    frames = 400
+    ebn = 1.0                                           # many frame errors -> the 40-error stop triggers
+    ref = o.monte_carlo(frames, ebn, 20, 25, 10, 0.3)
+    of, sigma = oracle_frames(o, frames, ebn)
+    dec = np.zeros((frames, o.N), np.int32); synd = np.zeros(frames, np.int32); it = np.zeros(frames, np.int32)
+    for f, fr in enumerate(of):
+        r = o.decode_frame(fr["llr"], 20, 25, 10, 0.3)
+        dec[f], synd[f], it[f] = r["decide"], r["synd"], r["iters"]
+    bits = np.stack([fr["nbin"] for fr in of])
+    stats = np.zeros(6, np.int64)
+    for lo in range(0, frames, 64):                      # batches, as the GPU driver feeds them
+        c.accumulate_stats(bits[lo:lo + 64], dec[lo:lo + 64], synd[lo:lo + 64], it[lo:lo + 64], stats)
+    assert ref[1] == 40 and stats[5] == 1
+    assert [int(x) for x in stats[:5]] == [ref[0], ref[1], ref[2], ref[3], ref[4]]
+    o.close()
+
+
+# ---- pass schedule -------------------------------------------------------------------------------
+class _Sched(C.Structure):
+    _fields_ = [("nsteps", C.c_int), ("step_ptr", C.POINTER(C.c_int)), ("order", C.POINTER(C.c_int)), ("depth", C.c_int)]
+
+
+@pytest.mark.parametrize("rel,cap,depth", [("matrices/N96_K48_GF64", 64, 4), ("matrices/Mat24_N480_M240", 16, 6),
+                                           ("matrices/MatDeclercq_R12_GF64", 64, 474), ("matrices/Ahmed_64800_R34_GF16", 8, 21),
+                                           ("matrices/AD_64800_R12_GF256", 64, 15), ("matrices/AD_64800_R12_GF256", 1, 15)])
+def test_schedule_preserves_reference_order(rel, cap, depth):
+    c = nbldpc.Code(matrix_path(rel))
+    L = nbldpc.lib()
+    s = _Sched()
+    L.nbgpu_build_schedule.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Sched)]
+    assert L.nbgpu_build_schedule(c.h, cap, C.byref(s)) == 0
+    assert s.depth == depth                              # SURVEY.md section 2.1 catalogue
+    sp = np.ctypeslib.as_array(s.step_ptr, (s.nsteps + 1,)).copy()
+    order = np.ctypeslib.as_array(s.order, (c.M,)).copy()
+    assert sorted(order.tolist()) == list(range(c.M)) and sp[0] == 0 and sp[-1] == c.M
+    assert (np.diff(sp) <= cap).all() and (np.diff(sp) >= 1).all()
+    step_of = np.zeros(c.M, np.int64)
+    for st in range(s.nsteps):
+        step_of[order[sp[st]:sp[st + 1]]] = st
+    last = np.full(c.N, -1, np.int64)                   # step of the latest (file order) check touching each variable
+    for m in range(c.M):
+        cols = c.col[c.row_ptr[m]:c.row_ptr[m + 1]]
+        assert (last[cols] < step_of[m]).all(), "check %d would run before/with an earlier check sharing a variable" % m
+        last[cols] = step_of[m]
