@@ -1,0 +1,396 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded info Mbit/s of the EMS NB-LDPC decode path at fixed iterations (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--frames B]
+
+A *step* is one pass of the hot path (NB_LDPC.c:266-474: intake, NbIterMax-1 layered EMS passes, decision,
+syndrome) over one batch of B synthetic frames per GPU.  One process per GPU (torchrun for N > 1); frames are
+independent, so the batch shards by frame with no data-path collective ("weak" scaling: B per GPU is fixed) and
+NCCL is used only for the barrier, the max-over-ranks time and one final all-reduce of the frame counters.
+
+`value`    whole-job info Mbit/s with the noisy frames already resident in HBM (device time, CUDA events).
+`e2e`      the same metric through the reference-facing C-ABI call nbgpu_decode_noisy with HOST buffers: H2D of the
+           received samples from pinned memory, decode, D2H of decisions/syndromes/iteration counts, every step.
+`roofline` HBM model of DESIGN.md section 4 for the decode kernel (the only kernel in a step).
+`cpu_baseline` / `--impl reference`  the reference's own CPU decoder (oracle/_ref/essai_probe = unmodified
+           NB_LDPC.c main loop, decode time only, Syndrom forced non-zero so all passes run) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# name -> (matrix, n_m, nb_oper, offset, Eb/N0, default frames per GPU per step)        
+WORKLOADS = {
+    "AD_64800_R12_GF256": ("matrices/AD_64800_R12_GF256", 20, 25, 0.3, 2.0, 2368),
+    "Ahmed_64800_R34_GF16": ("matrices/Ahmed_64800_R34_GF16", 16, 25, 0.3, 3.0, 4096),
+    "MatDeclercq_R12_GF64": ("matrices/MatDeclercq_R12_GF64", 20, 25, 0.3, 1.2, 4096),
+    "Mat24_N480_M240": ("matrices/Mat24_N480_M240", 16, 25, 0.3, 1.5, 65536),
+    "N96_K48_GF64": ("matrices/N96_K48_GF64", 20, 25, 0.3, 3.0, 1 << 20),
+}
+NB_ITER_MAX = 10
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def find_matrix(rel):
+    for d in (REF_DIR, "/root/reference"):
+        p = os.path.join(d, rel)
+        if os.path.exists(p):
+            return p
+    raise FileNotFoundError("%s not found under oracle/_ref (run __graft_entry__.build() where /root/reference exists)" % rel)
+
+
+def bytes_per_frame(N, E, q, n_m, passes):
+    """Algorithmic HBM bytes of one frame (SURVEY.md 8d / DESIGN.md 4): dense f32 APP rows read+written once per edge
+    visit, lossless compressed CtoV read+written once per edge visit, intake write, decisions."""
+    return N * q * 4 + passes * E * (2 * q * 4 + 2 * min(q * 4, 5 * n_m + 4)) + N
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.3 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference main loop on the host cores
+# -----------------------------------------------------------------------------------------------------------------
+def run_reference_cpu(wl, frames_per_proc, procs, seconds_hint=None):
+    """Runs `procs` concurrent copies of the reference (it is single-threaded; start.sh does the same) and returns
+    (aggregate frames/s over decode time, kind, sample description, wall seconds)."""
+    matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
+    exe = os.path.join(REF_DIR, "essai_probe")
+    if os.path.exists(exe):
+        with tempfile.TemporaryDirectory() as td:
+            os.makedirs(os.path.join(td, "data"), exist_ok=True)
+            os.symlink(os.path.join(REF_DIR, "matrices"), os.path.join(td, "matrices"))
+            ps = []
+            t0 = time.time()
+            for i in range(procs):
+                env = dict(os.environ, NBREF_FORCE="1", NBREF_LEVEL="0", NBREF_DIALECT="ubs",
+                           NBREF_SUMMARY=os.path.join(td, "sum%d.txt" % i))
+                env.pop("NBREF_TRACE", None)
+                ps.append(subprocess.Popen([exe, str(frames_per_proc), str(NB_ITER_MAX), matrix, str(ebn), str(n_m), str(offset),
+                                            str(nb_oper)], cwd=td, env=env, stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL,
+                                           stderr=subprocess.DEVNULL))
+            for p in ps:
+                p.wait()
+            wall = time.time() - t0
+            rate = 0.0
+            nfr = 0
+            for i in range(procs):
+                fr, dec_s, ch_s, passes = open(os.path.join(td, "sum%d.txt" % i)).read().split()[:4]
+                assert int(passes) == int(fr) * (NB_ITER_MAX - 1), "reference did not run the fixed number of passes"
+                rate += int(fr) / float(dec_s)
+                nfr += int(fr)
+        sample = "%d concurrent single-thread runs of the unmodified reference main loop (oracle/_ref/essai_probe), %d frames each, " \
+                 "decode time only (channel return -> last Syndrom), Syndrom forced non-zero -> %d passes/frame" % (
+                     procs, frames_per_proc, NB_ITER_MAX - 1)
+        return rate, "reference", sample, wall, nfr
+    # fallback: the oracle port (plain-C restatement), same sampling
+    import multiprocessing as mp
+    t0 = time.time()
+    with mp.Pool(procs) as pool:
+        res = pool.map(_port_worker, [(wl, frames_per_proc, i) for i in range(procs)])
+    wall = time.time() - t0
+    rate = sum(f / s for f, s in res)
+    sample = "%d processes of the oracle port (oracle/liboracle.so), %d frames each, decode time only, %d passes/frame" % (
+        procs, frames_per_proc, NB_ITER_MAX - 1)
+    return rate, "port", sample, wall, procs * frames_per_proc
+
+
+def _port_worker(arg):
+    wl, frames, idx = arg
+    import oracle_lib as ol
+    matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
+    o = ol.Oracle(find_matrix(matrix))
+    rng = np.random.default_rng(idx)
+    sigma = o.sigma(ebn)
+    tot = 0.0
+    for _ in range(frames):
+        noisy = (1.0 + sigma * rng.standard_normal((o.N, o.logGF))).astype(np.float32)
+        llr = o.channel_llr(noisy, sigma)
+        t0 = time.perf_counter()
+        o.decode_frame(llr, n_m, nb_oper, NB_ITER_MAX, offset, force=True)
+        tot += time.perf_counter() - t0
+    return frames, tot
+
+
+def cpu_sample_size(wl):
+    """frames per process so that one concurrent batch is roughly 10-30 s of CPU work per core"""
+    return {"AD_64800_R12_GF256": 4, "Ahmed_64800_R34_GF16": 10, "MatDeclercq_R12_GF64": 10, "Mat24_N480_M240": 400,
+            "N96_K48_GF64": 10000}[wl]
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import nbldpc
+    wl = args.workload
+    matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
+    code = nbldpc.Code(find_matrix(matrix))
+    cores = host_cores()
+    fpp = max(1, cpu_sample_size(wl) // 2)
+    for _ in range(min(args.warmup, 1)):
+        run_reference_cpu(wl, 1, cores)
+    rates, walls = [], []
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        rate, kind, sample, wall, nfr = run_reference_cpu(wl, fpp, cores)
+        rates.append(rate); walls.append(wall)
+    fps = statistics.mean(rates)
+    val = fps * code.info_bits / 1e6
+    line = {"impl": "reference", "metric": "decoded info Mbit/s at fixed iterations (%d passes)" % (NB_ITER_MAX - 1), "value": val,
+            "unit": "Mbit/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * statistics.mean(walls),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (reference's own drand48 frame stream)",
+            "frames_per_s": fps,
+            "config": config_dict(wl, code, fpp * cores, "host CPU only"),
+            "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(wl, code, frames, note):
+    matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
+    return {"workload": "%s: N=%d symbols over GF(%d) (%d code bits, %d info bits), M=%d, dc=%d, L-Bubble forward/backward EMS check node "
+                        "(CheckPassLogEMS), n_m=%d, nbOper=%d, offset=%.1f, NbIterMax=%d (= %d passes, early termination off), AWGN BPSK Eb/N0=%.1f dB"
+                        % (wl, code.N, code.q, code.N * code.logq, code.info_bits, code.M, code.dc_max, n_m, nb_oper, offset, NB_ITER_MAX,
+                           NB_ITER_MAX - 1, ebn),
+            "frames_per_step_per_gpu": frames, "cache": note}
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# our arm
+# -----------------------------------------------------------------------------------------------------------------
+def synth_frames(code, B, ebn, seed, pool=8):
+    """B received frames: `pool` codewords from the product's encoder (reference frame source), BPSK, plus white Gaussian
+    noise of the reference's sigma drawn with numpy (distinct per frame and per rank)."""
+    code.prepare_encoder()
+    code.rng_default()
+    code.rng_skip(seed * 7919)
+    bits = np.stack([code.random_codeword()[1] for _ in range(pool)])            # [pool, N, logq]
+    sigma = code.sigma(ebn)
+    rng = np.random.default_rng(1000 + seed)
+    idx = rng.integers(0, pool, B)
+    noisy = np.empty((B, code.N, code.logq), np.float32)
+    for lo in range(0, B, 256):
+        hi = min(B, lo + 256)
+        tx = 1.0 - 2.0 * bits[idx[lo:hi]].astype(np.float32)
+        noisy[lo:hi] = tx + np.float32(sigma) * rng.standard_normal(tx.shape, dtype=np.float32)
+    return noisy, bits[idx], sigma
+
+
+def ours(args, rank, local_rank, world):
+    import nbldpc
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if nbldpc.device_count() < 1:
+        raise RuntimeError("bench.py needs a B200: the product has no CPU fallback")
+    wl = args.workload
+    matrix, n_m, nb_oper, offset, ebn, dflt_B = WORKLOADS[wl]
+    B = args.frames or dflt_B
+    code = nbldpc.Code(find_matrix(matrix))
+    passes = NB_ITER_MAX - 1
+    dec = nbldpc.Decoder(code, n_m, nb_oper, NB_ITER_MAX, offset, early_stop=False, device=local_rank, max_batch=B,
+                         frames_per_cta=args.frames_per_cta, cns_per_step=args.cns_per_step)
+    geo = dec.geometry()
+    noisy, bits, sigma = synth_frames(code, B, ebn, rank)
+    nbldpc.pin(noisy)
+    out = (nbldpc.pin(np.zeros((B, code.N), np.int32)), nbldpc.pin(np.zeros(B, np.int32)), nbldpc.pin(np.zeros(B, np.int32)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- resident-input throughput (`value`) ----------------
+    dec.upload_noisy(noisy, sigma)
+    dec.sync()
+    for _ in range(args.warmup):
+        dec.run()
+    dec.sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    l0 = dec.launch_count()
+    t0 = time.time()
+    kms = []
+    dec.timer_begin()
+    for _ in range(args.steps):
+        dec.run()
+    ms = dec.timer_end()
+    t1 = time.time()
+    barrier()
+    launches = dec.launch_count() - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms = maxr(ms)
+    # per-launch duration of the decode kernel (CUDA events on the launching stream), outside the timed region
+    for _ in range(min(3, args.steps)):
+        dec.run()
+        kms.append(dec.last_kernel_ms())
+    kernel_ms = statistics.mean(kms)
+    d_res, s_res, it_res = dec.download()
+    frames_total = world * B * args.steps
+    fps = frames_total / (ms / 1e3)
+    value = fps * code.info_bits / 1e6
+
+    # ---------------- end to end through the C ABI with host buffers (`e2e`) ----------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        dec.decode_noisy_into(noisy, sigma, out)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.decode_noisy_into(noisy, sigma, out)
+    e2e_s = maxr(time.perf_counter() - e0)
+    barrier()
+    e2e_val = frames_total / e2e_s * code.info_bits / 1e6
+    assert (out[0] == d_res).all() and (out[2] == it_res).all(), "e2e and resident runs disagree"
+
+    # ---------------- counters: one NCCL all-reduce (the only collective of the path) ----------------
+    bit_err = int((bits[:, :code.K, :] != np.stack([code_bits(code, d_res[:, k]) for k in range(code.K)], axis=1)).sum()) if args.count_errors else -1
+    counters = np.array([B, int((s_res != 0).sum()), int(it_res.sum()), bit_err], np.int64)
+    if dist is not None:
+        import torch
+        t = torch.from_numpy(counters).cuda()
+        dist.all_reduce(t)
+        counters = t.cpu().numpy()
+
+    line = None
+    if rank == 0:
+        bpf = bytes_per_frame(code.N, code.E, code.q, n_m, passes)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bpf * B / (kernel_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("frames") == B:
+                traffic = tj.get("dram_bytes_per_launch")
+        line = {"metric": "decoded info Mbit/s at fixed iterations (%d passes)" % passes, "value": value, "unit": "Mbit/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic (encoder codewords + numpy Gaussian noise at the reference's sigma)",
+                "frames_per_s": fps,
+                "config": config_dict(wl, code, B, "per-step working set %.1f GB and inputs %.0f MB per GPU, both larger than the 126 MB L2 (no explicit flush)"
+                                      % (geo["slots"] * (code.N * code.q * 4 + code.E * geo["rec_stride"]) / 1e9, noisy.nbytes / 1e6)),
+                "geometry": geo,
+                "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": int(noisy.nbytes), "d2h_bytes_per_step": int(sum(o.nbytes for o in out)),
+                        "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                             "kernel": "decode_kernel<%d>" % code.q, "kernel_ms": kernel_ms, "bytes_per_frame": bpf, "frames_per_launch": B},
+                "clocks": clocks,
+                "counters": {"frames_per_step": int(counters[0]), "frames_nonzero_syndrome": int(counters[1]), "sum_iterations": int(counters[2]),
+                             "slow_path_selects": dec.slow_selects()}}
+        if world == 1 and not args.no_cpu:
+            cores = host_cores()
+            rate, kind, sample, wall, nfr = run_reference_cpu(wl, cpu_sample_size(wl), cores)
+            line["cpu_baseline"] = {"value": rate * code.info_bits / 1e6, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample,
+                                    "frames_per_s": rate, "wall_s": wall}
+        print(json.dumps(line), flush=True)
+    nbldpc.unpin(noisy)
+    for o in out:
+        nbldpc.unpin(o)
+    dec.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def code_bits(code, syms):
+    b = code.tables()[0]
+    return b[syms]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="AD_64800_R12_GF256", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (0 = workload default)")
+    ap.add_argument("--frames-per-cta", type=int, default=0)
+    ap.add_argument("--cns-per-step", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--count-errors", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,12 @@ def lib():
         "nbgpu_download": (C.c_int, [vp, _ip, _ip, _ip]),
         "nbgpu_last_kernel_ms": (C.c_int, [vp, _fp]),
         "nbgpu_launch_count": (C.c_long, [vp]),
+        "nbgpu_timer_begin": (C.c_int, [vp]),
+        "nbgpu_timer_end": (C.c_int, [vp, _fp]),
+        "nbgpu_host_register": (C.c_int, [vp, C.c_size_t]),
+        "nbgpu_host_unregister": (C.c_int, [vp]),
+        "nbgpu_geometry": (C.c_int, [vp, _ip]),
+        "nbgpu_slow_selects": (C.c_long, [vp]),
         "nbgpu_get_state": (C.c_int, [vp, C.c_int, _fp, _fp]),
         "nbgpu_check_node": (C.c_int, [vp, C.c_int, _fp, _ip, _fp, _ip, C.c_int]),
         "nbgpu_elementary_step": (C.c_int, [vp, _fp, _fp, _ip, _ip, _fp, _ip, C.c_int]),
@@ -235,6 +241,13 @@ class Decoder:
         self.B = B
         return d, s, it
 
+    def decode_noisy_into(self, noisy, sigma, out):
+        """nbgpu_decode_noisy on caller-owned (e.g. pinned) buffers, no allocation: noisy [B,N,logq] f32, out = (decide, synd, iters)."""
+        B = noisy.shape[0]
+        _check(lib().nbgpu_decode_noisy(self.h, _f(noisy), C.c_float(sigma), B, _i(out[0]), _i(out[1]), _i(out[2])), self.h)
+        self.B = B
+        return out
+
     def decode_llr(self, llr):
         llr = np.ascontiguousarray(llr, np.float32).reshape(-1, self.code.N, self.code.q)
         B = llr.shape[0]
@@ -271,6 +284,23 @@ class Decoder:
 
     def launch_count(self):
         return int(lib().nbgpu_launch_count(self.h))
+
+    def timer_begin(self):
+        _check(lib().nbgpu_timer_begin(self.h), self.h)
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        _check(lib().nbgpu_timer_end(self.h, C.byref(ms)), self.h)
+        return ms.value
+
+    def geometry(self):
+        g = np.zeros(8, np.int32)
+        _check(lib().nbgpu_geometry(self.h, _i(g)), self.h)
+        return dict(zip(("grid", "frames_per_cta", "cns_per_step", "steps_per_pass", "smem_bytes", "slots", "ctas_per_sm",
+                         "rec_stride"), [int(x) for x in g]))
+
+    def slow_selects(self):
+        return int(lib().nbgpu_slow_selects(self.h))
 
     def get_state(self, frame):
         app = np.zeros((self.code.N, self.code.q), np.float32)
@@ -335,6 +365,16 @@ class Decoder:
             self.close()
         except Exception:
             pass
+
+
+def pin(arr):
+    """Page-lock a numpy array in place (nbgpu_host_register); returns the array."""
+    _check(lib().nbgpu_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes))
+    return arr
+
+
+def unpin(arr):
+    _check(lib().nbgpu_host_unregister(C.c_void_p(arr.ctypes.data)))
 
 
 def device_count():

@@ -491,7 +491,8 @@ __global__ void channel_kernel(const KArgs a, const float *noisy, float *llr, fl
 struct nbgpu_ctx {
     int device;
     cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev0, ev1, ev_t0, ev_t1;
+    int per_sm;
     nbgpu_params p;
     KArgs k;
     int N, M, E, q, logq, dc_max;
@@ -586,6 +587,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     if (prop.major < 10) { ctx_err(c, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); free(c); return NBGPU_ECUDA; }
     CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(c, cudaEventCreate(&c->ev0)); CK(c, cudaEventCreate(&c->ev1));
+    CK(c, cudaEventCreate(&c->ev_t0)); CK(c, cudaEventCreate(&c->ev_t1));
 
     const int q = code->q, E = code->E, N = code->N, M = code->M;
     KArgs &k = c->k;
@@ -655,6 +657,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     else { CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<256>, NT, k.smem_bytes)); }
     if (per_sm < 1) { ctx_err(c, "decode kernel does not fit on an SM (smem %d bytes)", k.smem_bytes); nbgpu_destroy(c); return NBGPU_ECUDA; }
     if (getenv("NBGPU_CTAS_PER_SM")) per_sm = std::min(per_sm, atoi(getenv("NBGPU_CTAS_PER_SM")));
+    c->per_sm = per_sm;
     c->grid = prop.multiProcessorCount * per_sm;
     const int groups = (max_batch + k.F - 1) / k.F;
     if (c->grid > groups) c->grid = groups;
@@ -690,6 +693,8 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->stream) cudaStreamDestroy(c->stream);
     free(c->row_ptr_h); free(c->inv_h);
     free(c);
@@ -764,6 +769,50 @@ extern "C" int nbgpu_last_kernel_ms(nbgpu_ctx *c, float *ms)
     return NBGPU_OK;
 }
 extern "C" long nbgpu_launch_count(const nbgpu_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int nbgpu_timer_begin(nbgpu_ctx *c)
+{
+    if (!c) return NBGPU_EINVAL;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaEventRecord(c->ev_t0, c->stream));
+    return NBGPU_OK;
+}
+extern "C" int nbgpu_timer_end(nbgpu_ctx *c, float *ms)
+{
+    if (!c || !ms) return NBGPU_EINVAL;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaEventRecord(c->ev_t1, c->stream));
+    CK(c, cudaEventSynchronize(c->ev_t1));
+    CK(c, cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return NBGPU_OK;
+}
+extern "C" int nbgpu_host_register(void *ptr, size_t bytes)
+{
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); ctx_err(NULL, "cudaHostRegister failed: %s", cudaGetErrorString(e)); return NBGPU_ECUDA; }
+    return NBGPU_OK;
+}
+extern "C" int nbgpu_host_unregister(void *ptr)
+{
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); ctx_err(NULL, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); return NBGPU_ECUDA; }
+    return NBGPU_OK;
+}
+extern "C" int nbgpu_geometry(const nbgpu_ctx *c, int *geo)
+{
+    if (!c || !geo) return NBGPU_EINVAL;
+    geo[0] = c->grid; geo[1] = c->k.F; geo[2] = c->k.G / (c->k.F > 0 ? c->k.F : 1); geo[3] = c->k.nsteps;
+    geo[4] = c->k.smem_bytes; geo[5] = c->nslots; geo[6] = c->per_sm; geo[7] = c->k.rec_stride;
+    return NBGPU_OK;
+}
+extern "C" long nbgpu_slow_selects(nbgpu_ctx *c)
+{
+    if (!c) return -1;
+    unsigned v = 0;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+        cudaMemcpy(&v, c->d_slow, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (long)v;
+}
 
 extern "C" int nbgpu_download(nbgpu_ctx *c, int *decide, int *synd, int *iters)
 {

@@ -128,6 +128,17 @@ int nbgpu_download(nbgpu_ctx *ctx, int *decide, int *synd, int *iters);
 int nbgpu_last_kernel_ms(nbgpu_ctx *ctx, float *ms);
 /* number of kernels launched by this ctx since creation (bench.py gpu_launches) */
 long nbgpu_launch_count(const nbgpu_ctx *ctx);
+/* device-side stopwatch on the ctx stream (CUDA events): begin records, end records + waits + returns ms */
+int nbgpu_timer_begin(nbgpu_ctx *ctx);
+int nbgpu_timer_end(nbgpu_ctx *ctx, float *ms);
+/* page-lock / unlock a caller-owned host buffer so that the H2D/D2H copies of nbgpu_decode_* are DMA copies */
+int nbgpu_host_register(void *ptr, size_t bytes);
+int nbgpu_host_unregister(void *ptr);
+/* geometry chosen by nbgpu_create: geo[8] = grid (CTAs), frames per CTA group, check nodes per step,
+ * steps per pass, dynamic shared memory bytes, resident frame slots, CTAs per SM, record stride */
+int nbgpu_geometry(const nbgpu_ctx *ctx, int *geo);
+/* selection rows that needed the exact (slow) scan since creation; diagnostic */
+long nbgpu_slow_selects(nbgpu_ctx *ctx);
 
 /* Parity/debug: APP[N][q] and CtoV[E][q] (dense, as decoder_t.APP / decoder_t.CtoV) of one frame of
  * the last batch.  Only frames whose working set is still resident can be read (NBGPU_ESTATE). */

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.  Integer outputs
 (decisions, syndromes, iteration counts, symbols) and all float32 LLRs are required to be BIT-exact -- stricter
 than the 1e-5 relative tolerance BASELINE.json allows for message LLRs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -11,11 +13,27 @@ from common import (Golden, golden_names, matrix_path, oracle_frames, product_fr
 
 pytestmark = pytest.mark.gpu
 
-Q_CODES = {16: "matrices/Mat26_N48_M16", 64: "matrices/N96_K48_GF64", 256: "matrices/KN/N96_K48_GF256.txt"}
+Q_CODES = {16: "synthetic/GF16_N32_M8_dc8", 64: "matrices/N96_K48_GF64", 256: "matrices/KN/N96_K48_GF256.txt"}
+_SYN = {}
+
+
+def mpath(rel):
+    """reference matrices, plus small synthetic GF(16) codes (the only GF(16) matrix of the reference is the 64800-bit one)"""
+    if not rel.startswith("synthetic/"):
+        return matrix_path(rel)
+    if rel not in _SYN:
+        import re
+        import tempfile
+        q, N, M, dc = [int(x) for x in re.match(r"synthetic/GF(\d+)_N(\d+)_M(\d+)_dc(\d+)", rel).groups()]
+        a = random_regular_code(np.random.default_rng(q + N + dc), N, M, q, dc)
+        path = os.path.join(tempfile.mkdtemp(prefix="nbldpc_syn_"), rel.split("/")[1])
+        write_alist_ubs(path, a)
+        _SYN[rel] = path
+    return _SYN[rel]
 
 
 def _dec(rel, n_m, nb_oper=25, nb_iter_max=10, offset=0.3, **kw):
-    code = nbldpc.Code(matrix_path(rel))
+    code = nbldpc.Code(mpath(rel))
     return code, nbldpc.Decoder(code, n_m, nb_oper, nb_iter_max, offset, **kw)
 
 
@@ -45,7 +63,7 @@ def _rows(rng, B, q):
 @pytest.mark.parametrize("q,n_m", [(16, 16), (16, 6), (64, 20), (64, 32), (256, 20), (256, 5), (256, 32)])
 def test_select_nm(q, n_m):
     code, d = _dec(Q_CODES[q], n_m)
-    o = ol.Oracle(matrix_path(Q_CODES[q]), code.dialect)
+    o = ol.Oracle(mpath(Q_CODES[q]), code.dialect)
     rng = np.random.default_rng(q * 100 + n_m)
     rows = _rows(rng, 4000, q)
     gl, gg = d.select_nm(rows)
@@ -73,7 +91,7 @@ def _lists(rng, B, n_m, GF, short_frac=0.3):
 @pytest.mark.parametrize("q,n_m,nb_oper", [(16, 16, 25), (64, 20, 25), (64, 8, 6), (64, 5, 60), (256, 20, 25), (256, 32, 80)])
 def test_elementary_step(q, n_m, nb_oper):
     code, d = _dec(Q_CODES[q], n_m, nb_oper)
-    o = ol.Oracle(matrix_path(Q_CODES[q]), code.dialect)
+    o = ol.Oracle(mpath(Q_CODES[q]), code.dialect)
     rng = np.random.default_rng(7 + q + n_m)
     B = 3000
     a, ia = _lists(rng, B, n_m, q); b, ib = _lists(rng, B, n_m, q)
@@ -86,11 +104,12 @@ def test_elementary_step(q, n_m, nb_oper):
 
 @pytest.mark.parametrize("rel,n_m,nb_oper,offset", [("matrices/N96_K48_GF64", 20, 25, 0.3), ("matrices/Mat28_N72_M18", 12, 25, 1.0),
                                                     ("matrices/Mat212_N96_M16", 16, 20, 0.0), ("matrices/Mat26_N48_M16", 16, 25, 0.3),
+                                                    ("synthetic/GF16_N32_M8_dc8", 16, 25, 0.3), ("synthetic/GF16_N24_M12_dc4", 9, 25, 0.3),
                                                     ("matrices/KN/N96_K48_GF256.txt", 20, 25, 0.3),
                                                     ("matrices/KN/N576_K480_GF64.txt", 10, 14, 0.5)])
 def test_check_node_random(rel, n_m, nb_oper, offset):
     code, d = _dec(rel, n_m, nb_oper, 10, offset)
-    o = ol.Oracle(matrix_path(rel), code.dialect)
+    o = ol.Oracle(mpath(rel), code.dialect)
     rng = np.random.default_rng(3)
     for node in sorted(set(rng.integers(0, code.M, 6).tolist())):
         dc = int(code.row_deg[node])
@@ -122,7 +141,7 @@ def test_check_node_on_reference_messages(name):
 @pytest.mark.parametrize("q", [16, 64, 256])
 def test_channel_and_decision(q):
     code, d = _dec(Q_CODES[q], min(q, 16))
-    o = ol.Oracle(matrix_path(Q_CODES[q]), code.dialect)
+    o = ol.Oracle(mpath(Q_CODES[q]), code.dialect)
     fr, sigma = oracle_frames(o, 5, 2.0)
     noisy = np.stack([f["noisy"] for f in fr])
     llr, il, ig = d.channel(noisy, sigma, want_sorted=True)
@@ -175,10 +194,12 @@ def test_decode_equals_reference_run(name):
     ("matrices/N96_K48_GF64", 20, 25, 3.0, 64, False), ("matrices/Mat24_N480_M240", 16, 25, 1.5, 24, True),
     ("matrices/Mat26_N48_M16", 16, 25, 2.5, 200, True), ("matrices/Mat26_N48_M16", 6, 8, 2.5, 50, True),
     ("matrices/Mat212_N480_M80", 12, 18, 3.5, 12, True), ("matrices/KN/N128_K64_GF256.txt", 20, 25, 2.5, 60, True),
-    ("matrices/KN/N576_K480_GF64.txt", 16, 25, 4.0, 12, True)])
+    ("matrices/KN/N576_K480_GF64.txt", 16, 25, 4.0, 12, True),
+    ("synthetic/GF16_N32_M8_dc8", 16, 25, 4.0, 200, True), ("synthetic/GF16_N24_M12_dc4", 12, 25, 3.0, 200, True),
+    ("synthetic/GF256_N24_M12_dc4", 24, 30, 3.0, 40, True), ("synthetic/GF64_N60_M12_dc10", 14, 25, 5.0, 40, True)])
 def test_decode_batches_equal_oracle(rel, n_m, nb_oper, ebn, frames, early):
-    code = nbldpc.Code(matrix_path(rel))
-    o = ol.Oracle(matrix_path(rel), code.dialect)
+    code = nbldpc.Code(mpath(rel))
+    o = ol.Oracle(mpath(rel), code.dialect)
     fr, sigma = product_frames(code, frames, ebn)
     noisy = np.stack([f["noisy"] for f in fr])
     d = nbldpc.Decoder(code, n_m, nb_oper, 10, 0.3, early_stop=early, max_batch=frames)
