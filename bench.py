@@ -335,7 +335,7 @@ def ours(args, rank, local_rank, world):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (encoder codewords + numpy Gaussian noise at the reference's sigma)",
                 "frames_per_s": fps,
                 "config": config_dict(wl, code, B, "per-step working set %.1f GB and inputs %.0f MB per GPU, both larger than the 126 MB L2 (no explicit flush)"
-                                      % (geo["slots"] * (code.N * code.q * 4 + code.E * geo["rec_stride"]) / 1e9, noisy.nbytes / 1e6)),
+                                      % (geo["slots"] * (code.N * code.q * 4 + code.E * ((5 * n_m + 8 + 15) // 16 * 16)) / 1e9, noisy.nbytes / 1e6)),
                 "geometry": geo,
                 "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": int(noisy.nbytes), "d2h_bytes_per_step": int(sum(o.nbytes for o in out)),
                         "ms_per_step": 1e3 * e2e_s / args.steps},

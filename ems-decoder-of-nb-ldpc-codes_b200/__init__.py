@@ -296,8 +296,8 @@ class Decoder:
     def geometry(self):
         g = np.zeros(8, np.int32)
         _check(lib().nbgpu_geometry(self.h, _i(g)), self.h)
-        return dict(zip(("grid", "frames_per_cta", "cns_per_step", "steps_per_pass", "smem_bytes", "slots", "ctas_per_sm",
-                         "rec_stride"), [int(x) for x in g]))
+        return dict(zip(("grid", "frames_per_cta", "cns_per_step", "steps_per_pass", "smem_bytes", "slots", "warps_per_cta",
+                         "cns_per_warp"), [int(x) for x in g]))
 
     def slow_selects(self):
         return int(lib().nbgpu_slow_selects(self.h))

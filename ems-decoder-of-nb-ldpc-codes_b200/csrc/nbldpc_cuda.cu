@@ -1,24 +1,26 @@
 /*
  * nbldpc_cuda.cu -- CUDA layer + C ABI of the B200 EMS NB-LDPC decoder (sm_100a).
  *
- * One persistent CTA decodes one GROUP of F frames at a time, start to finish (all passes, early
- * termination included), pulling groups from an atomic work queue; the grid is a multiple of the SM
- * count.  A decoding pass walks the host-built step schedule (nbldpc_host.c): every step holds
- * check nodes that share no variable, so a CTA-wide barrier between steps reproduces the reference's
- * sequential layered update (NB_LDPC.c:320-466) bit for bit.  One step = three phases:
+ * One persistent CTA per SM decodes one GROUP of F frames at a time, start to finish (all passes,
+ * early termination included), pulling groups from an atomic work queue.  A decoding pass walks the
+ * host-built step schedule (nbldpc_host.c): every step holds check nodes that share no variable, so
+ * ONE CTA-wide barrier per step reproduces the reference's sequential layered update
+ * (NB_LDPC.c:320-466) bit for bit.  Inside a step every WARP owns a tile of up to cpw check nodes and
+ * runs them through three warp-private phases (no CTA barrier in between, lists in the warp's own
+ * shared memory):
  *
- *   phase 1  one WARP per edge   Mvc = APP - CtoV (NB_LDPC.c:334), top-n_m selection + normalisation
- *                                (:354-374), rotation by the edge coefficient (bubble_decoder.c:133)
- *   phase 2  one THREAD per ElementaryStep: forward/backward chains, then the merges
- *                                (bubble_decoder.c:157-227, 316-593)
- *   phase 3  one WARP per edge   saturation + offset, expansion to the dense q-vector
- *                                (bubble_decoder.c:231-281), CtoV store, APP = Mcv + Mvc
- *                                (NB_LDPC.c:415-450), fused Decision (tools.c:312)
+ *   phase 1  warp per edge, NE edges interleaved:  Mvc = APP - CtoV (NB_LDPC.c:334), top-n_m
+ *            selection + normalisation (:354-374), rotation by the edge coefficient (bubble_decoder.c:133)
+ *   phase 2  THREAD per ElementaryStep, 4 task slots per check node: forward/backward chains with the
+ *            merges folded into the rounds where their inputs are ready (bubble_decoder.c:157-227, 316-593)
+ *   phase 3  warp per edge, NE edges interleaved:  Mvc recomputed (same two operands, same result),
+ *            saturation + offset + expansion to the dense q-vector (bubble_decoder.c:231-281), CtoV
+ *            store, APP = Mcv + Mvc (NB_LDPC.c:415-450), fused Decision (tools.c:312)
  *
  * HBM layout per resident frame (slot): APP[N][q] f32 (row = 4q bytes, one coalesced warp access);
  * CtoV as one lossless record per edge {llr[n_m] f32, sat f32, stp i32, sym[n_m] u8} -- a dense CtoV
  * row is "stp explicit (symbol, LLR) pairs + one constant" (bubble_decoder.c:262-270); decisions u8.
- * Between phase 1 and 3 the APP row temporarily holds the un-normalised Mvc (NB_LDPC.c:448 needs it).
+ * Every APP row is read twice (L2 hit the second time) and written once per edge visit.
  */
 #include "nbldpc_device.cuh"
 #include "nbldpc_internal.h"
@@ -29,89 +31,44 @@
 #include <algorithm>
 #include <vector>
 
-#define NT 256            /* threads per CTA */
-#define NW (NT / 32)
+#define NT_MAX 512        /* threads per CTA (upper bound; the plan may use fewer warps) */
+#define NE 2              /* edges interleaved per warp in phases 1 and 3 */
+#define UNIT_NT 256       /* block size of the small unit-boundary kernels */
 
 struct KArgs {
     int N, M, E, q, logq, dc_max;
     int n_m, nb_oper, passes, early_stop, nb_iter_max;
     float offset;
-    int F, G, nsteps, L, tasks;        /* frames per group, items per step, lists per item, ES tasks */
+    int F, nw, cpw, cap, nsteps, L;     /* frames per group, warps per CTA, check nodes per warp, items per step, steps, lists per node */
     int B, input_kind;                  /* 0 = noisy samples, 1 = dense LLR */
     double den;                         /* 2.0 * (double)(float)(sigma*sigma), channel.c:73 */
-    const int *row_ptr, *col, *order, *step_ptr, *isolated;
+    const int *step_ptr, *isolated;
     int n_isolated;
-    const uint8_t *hval, *last, *rotin, *rotout, *img, *inv;
+    const uint32_t *cninfo;             /* [M] schedule order: first edge | degree << 24            */
+    const uint32_t *einfo;              /* [E] variable | coefficient << 20 | last-visit flag << 28 */
+    const int *row_ptr, *col;
+    const uint8_t *hval, *rotin, *rotout, *img, *inv;
+    int gf_closed;
     const float *in;
     float *app; uint8_t *ctov; uint8_t *dec;
     int rec_stride;
     int *out_decide, *out_synd, *out_iters, *frame_slot, *slot_frame;
     unsigned *queue, *slow_counter;
-    /* shared memory carve-up (byte offsets) */
-    int off_llr, off_sym, off_len, off_mask, off_ws, off_misc, smem_bytes;
+    /* shared memory map (bytes): tables | misc | per-warp scratch areas | per-warp lists */
+    int off_tab, off_misc, off_wa, wa_bytes, off_wb, wb_bytes;
+    int wa_sel, wa_mask, wa_meta;       /* offsets inside a warp's scratch area (scr at 0) */
+    int wb_sym, wb_len;                 /* offsets inside a warp's list area (llr at 0) */
+    int smem_bytes;
 };
 
-__device__ __forceinline__ float rec_sat(const uint8_t *rec, int n_m) { return *reinterpret_cast<const float *>(rec + 4 * n_m); }
-__device__ __forceinline__ int rec_stp(const uint8_t *rec, int n_m) { return *reinterpret_cast<const int *>(rec + 4 * n_m + 4); }
-
-/* dense CtoV values of this lane's symbols from the record (through ws.row) */
-template <int Q>
-__device__ __forceinline__ void expand_record(const uint8_t *rec, int n_m, int lane, WarpScratch<Q> &ws,
-                                              float (&c)[QTraits<Q>::VPL])
-{
-    constexpr int VPL = QTraits<Q>::VPL;
-    const int stp = rec_stp(rec, n_m);
-    const float sat = rec_sat(rec, n_m);
-    if (stp == 0) {
-#pragma unroll
-        for (int j = 0; j < VPL; j++) c[j] = sat;
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < VPL; j++) ws.row[lane * VPL + j] = sat;
-    __syncwarp();
-    if (lane < stp) ws.row[rec[4 * n_m + 8 + lane]] = reinterpret_cast<const float *>(rec)[lane];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < VPL; j++) c[j] = ws.row[lane * VPL + j];
-    __syncwarp();
-}
-
-/* phase 3 core: from the check node's output list of one edge (binary-image symbols) build the record
- * and the dense Mcv values of this lane (bubble_decoder.c:231-281). */
-template <int Q>
-__device__ __forceinline__ void finish_edge(const float *lo, const uint8_t *so, int len, const uint8_t *rotout_h,
-                                            int n_m, float offset, int lane, WarpScratch<Q> &ws, uint8_t *rec,
-                                            float (&mcv)[QTraits<Q>::VPL])
-{
-    constexpr int VPL = QTraits<Q>::VPL;
-    const int stp = len;                                         /* first absent entry, :233-243 */
-    float llr = NB_SENT; int sym = 0;
-    if (lane < stp) { llr = lo[lane]; sym = rotout_h[so[lane]]; }   /* DIVGF by the coefficient, :249-254 */
-    const float last = __shfl_sync(NB_FULL, llr, max(stp - 1, 0));
-    const float sat = __fadd_rn(stp > 0 ? last : NB_SENT, offset);  /* :264 (stp == 0 cannot occur) */
-    if (rec) {
-        if (lane < n_m) { reinterpret_cast<float *>(rec)[lane] = llr; rec[4 * n_m + 8 + lane] = (uint8_t)sym; }
-        if (lane == 0) { *reinterpret_cast<float *>(rec + 4 * n_m) = sat; *reinterpret_cast<int *>(rec + 4 * n_m + 4) = stp; }
-    }
-#pragma unroll
-    for (int j = 0; j < VPL; j++) ws.row[lane * VPL + j] = sat;
-    __syncwarp();
-    if (lane < stp) ws.row[sym] = llr;                           /* :267-270 */
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < VPL; j++) mcv[j] = ws.row[lane * VPL + j];
-    __syncwarp();
-}
-
-/* list addressing inside the CTA's shared memory */
+/* list addressing inside a warp's shared memory; c = check node of the warp's tile */
 struct Lists {
     float *llr; uint8_t *sym; uint8_t *len; int L, n_m;
-    __device__ __forceinline__ float *l(int item, int li) const { return llr + (item * L + li) * n_m; }
-    __device__ __forceinline__ uint8_t *s(int item, int li) const { return sym + (item * L + li) * n_m; }
-    __device__ __forceinline__ uint8_t &n(int item, int li) const { return len[item * L + li]; }
+    __device__ __forceinline__ float *l(int c, int li) const { return llr + (c * L + li) * n_m; }
+    __device__ __forceinline__ uint8_t *s(int c, int li) const { return sym + (c * L + li) * n_m; }
+    __device__ __forceinline__ uint8_t &n(int c, int li) const { return len[c * L + li]; }
 };
-/* list ids of one item with degree dc: U[t] = t; F after s steps = dc+s-1 (s>=1); B after s steps =
+/* list ids of one node with degree dc: U[t] = t; F after s steps = dc+s-1 (s>=1); B after s steps =
  * dc+(dc-2)+s-1; merge k = dc+2(dc-2)+k  (bubble_decoder.c:166-227: MatriceInter rows) */
 __device__ __forceinline__ int id_F(int dc, int s) { return s == 0 ? 0 : dc + s - 1; }
 __device__ __forceinline__ int id_B(int dc, int s) { return s == 0 ? dc - 1 : dc + (dc - 2) + s - 1; }
@@ -124,25 +81,80 @@ __device__ __forceinline__ int id_out(int dc, int t)
     return id_M(dc, t - 1);
 }
 
-/* forward (dir 0) or backward (dir 1) chain of one check node: dc-2 sequential elementary steps */
-__device__ __forceinline__ void chain_task(const Lists &ls, int item, int dc, int dir, uint32_t *mask, int mstride,
-                                           int mwords, int nb_oper)
+/* a warp's private shared memory */
+template <int Q> struct WarpMem {
+    uint32_t *scr[NE];       /* per in-flight edge: sorted keys / dense row               */
+    uint32_t *sel[NE];       /* winners of the selection rounds                            */
+    uint32_t *mask;          /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided  */
+    int4 *meta;              /* [cpw] {first edge, degree (0 = skip), frame, -}            */
+    Lists ls;
+    __device__ __forceinline__ WarpMem(unsigned char *smem, const KArgs &a, int warp)
+    {
+        unsigned char *wa = smem + a.off_wa + warp * a.wa_bytes;
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            scr[e] = reinterpret_cast<uint32_t *>(wa) + e * QTraits<Q>::SCR_WORDS;
+            sel[e] = reinterpret_cast<uint32_t *>(wa + a.wa_sel) + e * 36;
+        }
+        mask = reinterpret_cast<uint32_t *>(wa + a.wa_mask);
+        meta = reinterpret_cast<int4 *>(wa + a.wa_meta);
+        unsigned char *wb = smem + a.off_wb + warp * a.wb_bytes;
+        ls.llr = reinterpret_cast<float *>(wb);
+        ls.sym = wb + a.wb_sym;
+        ls.len = wb + a.wb_len;
+        ls.L = a.L; ls.n_m = a.n_m;
+    }
+};
+
+/* ---- phase 2: all elementary steps of the cnt check nodes of a warp's tile ----
+ * Round r = 1..dcmax-2.  Slot 0/1 of a node: forward/backward chain step r (bubble_decoder.c:166-200).
+ * Slots 2/3: the merges ES(F_k, B_{dc-3-k}) (:217-227) whose later input appears in round r-1:
+ * k = r-1 (if k >= dc-3-k) and k = dc-2-r (if dc-3-k = r-1 > k). */
+template <int Q>
+__device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const int4 *meta, int cnt, int dcmax, uint32_t *mask,
+                                                      int lane, int nb_oper)
 {
-    for (int kk = 1; kk <= dc - 2; kk++) {
-        const int a = dir ? id_B(dc, kk - 1) : id_F(dc, kk - 1);
-        const int b = dir ? dc - 1 - kk : kk;
-        const int o = dir ? id_B(dc, kk) : id_F(dc, kk);
-        ls.n(item, o) = (uint8_t)es_serial(ls.l(item, a), ls.s(item, a), ls.n(item, a), ls.l(item, b), ls.s(item, b),
-                                           ls.n(item, b), ls.l(item, o), ls.s(item, o), mask, mstride, mwords, ls.n_m, nb_oper);
+    for (int r = 1; r <= dcmax - 2; r++) {
+        for (int cb = 0; cb < cnt; cb += 8) {
+            const int c = cb + (lane >> 2), slot = lane & 3;
+            if (c < cnt) {
+                const int dc = meta[c].y;
+                int a = 0, b = 0, o = 0;
+                bool valid = false;
+                if (slot == 0) { valid = r <= dc - 2; a = id_F(dc, r - 1); b = r; o = id_F(dc, r); }
+                else if (slot == 1) { valid = r <= dc - 2; a = id_B(dc, r - 1); b = dc - 1 - r; o = id_B(dc, r); }
+                else {
+                    const int k = (slot == 2) ? r - 1 : dc - 2 - r;
+                    valid = (slot == 2) ? (k <= dc - 3 && 2 * k >= dc - 3) : (k >= 0 && k <= dc - 3 && r - 1 > k);
+                    a = id_F(dc, k); b = id_B(dc, dc - 3 - k); o = id_M(dc, k);
+                }
+                if (valid)
+                    ls.n(c, o) = (uint8_t)es_serial<Q>(ls.l(c, a), ls.s(c, a), ls.n(c, a), ls.l(c, b), ls.s(c, b), ls.n(c, b),
+                                                       ls.l(c, o), ls.s(c, o), mask + lane, 32, ls.n_m, nb_oper);
+            }
+            __syncwarp();
+        }
     }
 }
-/* merge k: ElementaryStep(F after k steps, B after dc-3-k steps) -> output of edge k+1 */
-__device__ __forceinline__ void merge_task(const Lists &ls, int item, int dc, int k, uint32_t *mask, int mstride,
-                                           int mwords, int nb_oper)
+
+/* phase 3 core: from the check node's output list of one edge (binary-image symbols) build the
+ * record entry of this lane and the saturation constant (bubble_decoder.c:231-264). */
+template <int Q>
+__device__ __forceinline__ RecView finish_list(const float *lo, const uint8_t *so, int len, int h, const GFTab &gf,
+                                               float offset, int lane)
 {
-    const int a = id_F(dc, k), b = id_B(dc, dc - 3 - k), o = id_M(dc, k);
-    ls.n(item, o) = (uint8_t)es_serial(ls.l(item, a), ls.s(item, a), ls.n(item, a), ls.l(item, b), ls.s(item, b),
-                                       ls.n(item, b), ls.l(item, o), ls.s(item, o), mask, mstride, mwords, ls.n_m, nb_oper);
+    RecView r;
+    r.stp = len;                                                     /* first absent entry, :233-243 */
+    r.llr = NB_SENT; r.sym = 0;
+    if (lane < len) { r.llr = lo[lane]; r.sym = gf_rot_out<Q>(gf, so[lane], h); }   /* DIVGF by the coefficient, :249-254 */
+    const float last = __shfl_sync(NB_FULL, r.llr, max(len - 1, 0));
+    r.sat = __fadd_rn(len > 0 ? last : NB_SENT, offset);             /* :264 (len == 0 cannot occur) */
+    return r;
+}
+__device__ __forceinline__ void store_record(uint8_t *rec, const RecView &r, int n_m, int lane)
+{
+    if (lane < n_m) { reinterpret_cast<float *>(rec)[lane] = r.llr; rec[4 * n_m + 8 + lane] = (uint8_t)r.sym; }
+    if (lane == 0) *reinterpret_cast<int2 *>(rec + 4 * n_m) = make_int2(__float_as_int(r.sat), r.stp);
 }
 
 /* LLR intake for one variable (channel.c:66-76), one warp: lanes < 2*logq first build the per-bit
@@ -150,11 +162,10 @@ __device__ __forceinline__ void merge_task(const Lists &ls, int item, int dc, in
  * reference's float <- double + double rounding. */
 template <int Q>
 __device__ __forceinline__ void intake_variable(const float *noisy_n, double den, const uint8_t *img, int lane,
-                                                WarpScratch<Q> &ws, float (&v)[QTraits<Q>::VPL])
+                                                double *t, float (&v)[QTraits<Q>::VPL])
 {
     constexpr int VPL = QTraits<Q>::VPL;
     constexpr int LOGQ = QTraits<Q>::LOGQ;
-    double *t = reinterpret_cast<double *>(ws.row);
     if (lane < 2 * LOGQ) {
         const float y = noisy_n[lane >> 1];
         const float s = (lane & 1) ? -1.0f : 1.0f;                 /* BPSK(b) = 1 - 2b */
@@ -177,19 +188,23 @@ __device__ __forceinline__ void intake_variable(const float *noisy_n, double den
     __syncwarp();
 }
 
+__device__ __forceinline__ void load_gf_tables(unsigned char *smem, const KArgs &a, GFTab &gf)
+{
+    uint8_t *tab = smem + a.off_tab;
+    for (int i = threadIdx.x; i < a.q; i += blockDim.x) { tab[i] = a.img[i]; tab[256 + i] = a.inv[i]; }
+    gf.img = tab; gf.inv = tab + 256; gf.rotin = a.rotin; gf.rotout = a.rotout; gf.closed = a.gf_closed;
+}
+
 template <int Q>
-__global__ void __launch_bounds__(NT, 2) decode_kernel(const KArgs a)
+__global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     extern __shared__ __align__(16) unsigned char smem[];
-    Lists ls;
-    ls.llr = reinterpret_cast<float *>(smem + a.off_llr);
-    ls.sym = smem + a.off_sym;
-    ls.len = smem + a.off_len;
-    ls.L = a.L; ls.n_m = a.n_m;
-    uint32_t *masks = reinterpret_cast<uint32_t *>(smem + a.off_mask);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpScratch<Q> &ws = reinterpret_cast<WarpScratch<Q> *>(smem + a.off_ws)[warp];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+    WarpMem<Q> wm(smem, a, warp);
+    const Lists &ls = wm.ls;
+    GFTab gf;
+    load_gf_tables(smem, a, gf);
     int *misc = reinterpret_cast<int *>(smem + a.off_misc);
     int *s_base = misc;                 /* [1]  first frame of the group  */
     int *s_alive = misc + 1;            /* [1]  frames of the group still iterating */
@@ -197,36 +212,34 @@ __global__ void __launch_bounds__(NT, 2) decode_kernel(const KArgs a)
     int *s_badrow = misc + 2 + a.F;     /* [F]  first check row with non-zero syndrome */
     int *s_synd = misc + 2 + 2 * a.F;   /* [F]  last syndrome value */
     const int F = a.F, N = a.N, n_m = a.n_m, dcm = a.dc_max;
-    const int mwords = (Q + 31) / 32;
     const size_t slot_app = (size_t)F * N * Q;
     float *app = a.app + blockIdx.x * slot_app;
     uint8_t *ctov = a.ctov + (size_t)blockIdx.x * F * a.E * a.rec_stride;
     uint8_t *dec = a.dec + (size_t)blockIdx.x * F * N;
 
     for (;;) {
+        __syncthreads();
         if (tid == 0) *s_base = (int)atomicAdd(a.queue, (unsigned)F);
         __syncthreads();
         const int base = *s_base;
         if (base >= a.B) break;
         const int nf = min(F, a.B - base);
         /* ---------------- frame initialisation: NB_LDPC.c:273-288 + channel.c:66-76 ---------------- */
-        for (int w = warp; w < nf * N; w += NW) {
+        for (int w = warp; w < nf * N; w += nw) {
             const int f = w / N, n = w - f * N;
             float v[VPL];
-            if (a.input_kind == 0) intake_variable<Q>(a.in + ((size_t)(base + f) * N + n) * a.logq, a.den, a.img, lane, ws, v);
+            if (a.input_kind == 0) intake_variable<Q>(a.in + ((size_t)(base + f) * N + n) * a.logq, a.den, gf.img, lane,
+                                                      reinterpret_cast<double *>(wm.scr[0]), v);
             else load_row<Q>(a.in + ((size_t)(base + f) * N + n) * Q, lane, v);
             store_row<Q>(app + ((size_t)f * N + n) * Q, lane, v);
         }
-        for (int i = tid; i < nf * a.E; i += NT) {           /* CtoV = 0: stp 0, constant 0.0f */
-            uint8_t *rec = ctov + (size_t)i * a.rec_stride;
-            *reinterpret_cast<float *>(rec + 4 * n_m) = 0.0f;
-            *reinterpret_cast<int *>(rec + 4 * n_m + 4) = 0;
-        }
-        for (int i = tid; i < F; i += NT) { s_done[i] = (i < nf) ? 0 : -1; s_synd[i] = 0; }
+        for (int i = tid; i < nf * a.E; i += nthr)           /* CtoV = 0: stp 0, constant 0.0f */
+            *reinterpret_cast<int2 *>(ctov + (size_t)i * a.rec_stride + 4 * n_m) = make_int2(0, 0);
+        for (int i = tid; i < F; i += nthr) { s_done[i] = (i < nf) ? 0 : -1; s_synd[i] = 0; }
         if (tid == 0) { *s_alive = nf; for (int f = 0; f < nf; f++) { a.frame_slot[base + f] = blockIdx.x * F + f; a.slot_frame[blockIdx.x * F + f] = base + f; } }
         __syncthreads();
         /* variables that no check node touches keep their channel decision */
-        for (int w = warp; w < nf * a.n_isolated; w += NW) {
+        for (int w = warp; w < nf * a.n_isolated; w += nw) {
             const int f = w / a.n_isolated, n = a.isolated[w - f * a.n_isolated];
             float v[VPL];
             load_row<Q>(app + ((size_t)f * N + n) * Q, lane, v);
@@ -238,102 +251,129 @@ __global__ void __launch_bounds__(NT, 2) decode_kernel(const KArgs a)
             for (int st = 0; st < a.nsteps; st++) {
                 const int c0 = a.step_ptr[st], ncn = a.step_ptr[st + 1] - c0;
                 const int items = ncn * nf;                   /* item = f * ncn + ci */
+                const int per = (items + nw - 1) / nw;        /* <= cpw by construction of the schedule */
+                const int first = warp * per;
+                const int cnt = max(0, min(per, items - first));
                 /* ---------------- phase 1 ---------------- */
-                for (int w = warp; w < items * dcm; w += NW) {
-                    const int item = w / dcm, t = w - item * dcm;
-                    const int f = item / ncn, cn = a.order[c0 + item - f * ncn];
-                    const int e0 = a.row_ptr[cn], dc = a.row_ptr[cn + 1] - e0;
-                    if (t >= dc || s_done[f]) continue;
-                    const int e = e0 + t;
-                    float *row = app + ((size_t)f * N + a.col[e]) * Q;
-                    const uint8_t *rec = ctov + ((size_t)f * a.E + e) * a.rec_stride;
-                    float v[VPL], c[VPL];
-                    load_row<Q>(row, lane, v);
-                    expand_record<Q>(rec, n_m, lane, ws, c);
+                {
+                    int f = cnt > 0 ? first / ncn : 0, ci = first - f * ncn;
+                    for (int c = 0; c < cnt; c++) {
+                        const uint32_t info = a.cninfo[c0 + ci];
+                        const int e0 = info & 0xffffff;
+                        const int dc = s_done[f] ? 0 : (int)(info >> 24);
+                        if (lane == 0) wm.meta[c] = make_int4(e0, dc, f, 0);
+                        for (int t = 0; t < dc; t += NE) {
+                            float v[NE][VPL];
+                            RecView r[NE];
+                            int hv[NE];
 #pragma unroll
-                    for (int j = 0; j < VPL; j++) v[j] = __fsub_rn(v[j], c[j]);           /* NB_LDPC.c:334 */
-                    store_row<Q>(row, lane, v);
-                    store_row<Q>(ws.row, lane, v);
-                    float llr; int sym;
-                    warp_select_nm<Q>(v, lane, ws, n_m, llr, sym, a.slow_counter);
-                    if (lane < n_m) {
-                        ls.l(item, t)[lane] = llr;
-                        ls.s(item, t)[lane] = a.rotin[a.hval[e] * Q + sym];                /* bubble_decoder.c:145 */
+                            for (int e = 0; e < NE; e++) {
+                                const bool valid = t + e < dc;
+                                const int ed = e0 + min(t + e, dc - 1);
+                                const uint32_t ei = a.einfo[ed];
+                                hv[e] = (ei >> 20) & 0xff;
+                                load_row<Q>(app + ((size_t)f * N + (ei & 0xfffff)) * Q, lane, v[e]);
+                                r[e] = load_record(ctov + ((size_t)f * a.E + ed) * a.rec_stride, n_m, lane);
+                                if (!valid) r[e].stp = 0;     /* duplicate of the previous edge: result ignored */
+                            }
+#pragma unroll
+                            for (int e = 0; e < NE; e++) {
+                                float cv[VPL];
+                                expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
+#pragma unroll
+                                for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
+                            }
+                            float llr[NE]; int sym[NE];
+                            select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
+#pragma unroll
+                            for (int e = 0; e < NE; e++) {
+                                if (t + e < dc) {
+                                    if (lane < n_m) {
+                                        ls.l(c, t + e)[lane] = llr[e];
+                                        ls.s(c, t + e)[lane] = (uint8_t)gf_rot_in<Q>(gf, sym[e], hv[e]);   /* bubble_decoder.c:145 */
+                                    }
+                                    if (lane == 0) ls.n(c, t + e) = (uint8_t)n_m;
+                                }
+                            }
+                        }
+                        if (++ci == ncn) { ci = 0; f++; }
                     }
-                    if (lane == 0) ls.n(item, t) = (uint8_t)n_m;
                 }
-                __syncthreads();
-                /* ---------------- phase 2a: forward / backward chains ---------------- */
-                for (int task = tid; task < items * 2; task += NT) {
-                    const int item = task >> 1, f = item / ncn, cn = a.order[c0 + item - f * ncn];
-                    const int dc = a.row_ptr[cn + 1] - a.row_ptr[cn];
-                    if (s_done[f]) continue;
-                    chain_task(ls, item, dc, task & 1, masks + (task % a.tasks), a.tasks, mwords, a.nb_oper);
-                }
-                __syncthreads();
-                /* ---------------- phase 2b: merges ---------------- */
-                if (dcm > 2) {
-                    for (int task = tid; task < items * (dcm - 2); task += NT) {
-                        const int item = task / (dcm - 2), k = task - item * (dcm - 2);
-                        const int f = item / ncn, cn = a.order[c0 + item - f * ncn];
-                        const int dc = a.row_ptr[cn + 1] - a.row_ptr[cn];
-                        if (k >= dc - 2 || s_done[f]) continue;
-                        merge_task(ls, item, dc, k, masks + (task % a.tasks), a.tasks, mwords, a.nb_oper);
-                    }
-                    __syncthreads();
-                }
+                __syncwarp();
+                /* ---------------- phase 2 ---------------- */
+                tile_elementary_steps<Q>(ls, wm.meta, cnt, dcm, wm.mask, lane, a.nb_oper);
                 /* ---------------- phase 3 ---------------- */
-                for (int w = warp; w < items * dcm; w += NW) {
-                    const int item = w / dcm, t = w - item * dcm;
-                    const int f = item / ncn, cn = a.order[c0 + item - f * ncn];
-                    const int e0 = a.row_ptr[cn], dc = a.row_ptr[cn + 1] - e0;
-                    if (t >= dc || s_done[f]) continue;
-                    const int e = e0 + t, var = a.col[e];
-                    float *row = app + ((size_t)f * N + var) * Q;
-                    uint8_t *rec = ctov + ((size_t)f * a.E + e) * a.rec_stride;
-                    const int lo_id = id_out(dc, t);
-                    float mcv[VPL], v[VPL];
-                    load_row<Q>(row, lane, v);                                             /* Mvc parked by phase 1 */
-                    finish_edge<Q>(ls.l(item, lo_id), ls.s(item, lo_id), ls.n(item, lo_id), a.rotout + a.hval[e] * Q,
-                                   n_m, a.offset, lane, ws, rec, mcv);
+                for (int c = 0; c < cnt; c++) {
+                    const int4 mt = wm.meta[c];
+                    const int e0 = mt.x, dc = mt.y, f = mt.z;
+                    for (int t = 0; t < dc; t += NE) {
+                        float v[NE][VPL];
+                        RecView r[NE];
+                        uint32_t ei[NE];
 #pragma unroll
-                    for (int j = 0; j < VPL; j++) v[j] = __fadd_rn(mcv[j], v[j]);          /* NB_LDPC.c:448 */
-                    store_row<Q>(row, lane, v);
-                    if (a.last[e]) {                                                       /* tools.c:312 fused */
-                        const int d = warp_argmin<Q>(v, lane);
-                        if (lane == 0) dec[f * N + var] = (uint8_t)d;
+                        for (int e = 0; e < NE; e++) {
+                            const int ed = e0 + min(t + e, dc - 1);
+                            ei[e] = a.einfo[ed];
+                            load_row<Q>(app + ((size_t)f * N + (ei[e] & 0xfffff)) * Q, lane, v[e]);
+                            r[e] = load_record(ctov + ((size_t)f * a.E + ed) * a.rec_stride, n_m, lane);
+                        }
+#pragma unroll
+                        for (int e = 0; e < NE; e++) {
+                            float cv[VPL];
+                            expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
+#pragma unroll
+                            for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);          /* Mvc again, NB_LDPC.c:334 */
+                        }
+                        __syncwarp();                          /* every lane has consumed the old records */
+#pragma unroll
+                        for (int e = 0; e < NE; e++) {
+                            if (t + e < dc) {
+                                const int ed = e0 + t + e, var = ei[e] & 0xfffff, lo_id = id_out(dc, t + e);
+                                const RecView nr = finish_list<Q>(ls.l(c, lo_id), ls.s(c, lo_id), ls.n(c, lo_id), (ei[e] >> 20) & 0xff,
+                                                                  gf, a.offset, lane);
+                                store_record(ctov + ((size_t)f * a.E + ed) * a.rec_stride, nr, n_m, lane);
+                                float mcv[VPL];
+                                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr[e]), mcv);     /* :262-281 */
+#pragma unroll
+                                for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
+                                store_row<Q>(app + ((size_t)f * N + var) * Q, lane, v[e]);
+                                if (ei[e] >> 28) {                                                     /* tools.c:312 fused */
+                                    const int d = warp_argmin<Q>(v[e], lane);
+                                    if (lane == 0) dec[f * N + var] = (uint8_t)d;
+                                }
+                            }
+                        }
                     }
                 }
                 __syncthreads();
             }
             /* ---------------- Syndrom (tools.c:284-299) + early termination (NB_LDPC.c:470) ---------------- */
-            for (int i = tid; i < nf; i += NT) s_badrow[i] = a.M;
+            for (int i = tid; i < nf; i += nthr) s_badrow[i] = a.M;
             __syncthreads();
-            for (int i = tid; i < nf * a.M; i += NT) {
+            for (int i = tid; i < nf * a.M; i += nthr) {
                 const int f = i / a.M, m = i - f * a.M;
                 if (s_done[f]) continue;
                 int x = 0;
-                for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= a.rotin[a.hval[e] * Q + dec[f * N + a.col[e]]];
+                for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= gf_rot_in<Q>(gf, dec[f * N + a.col[e]], a.hval[e]);
                 if (x) atomicMin(&s_badrow[f], m);
             }
             __syncthreads();
             if (tid < nf && !s_done[tid]) {
                 const int f = tid, m = s_badrow[f];
                 int x = 0;
-                if (m < a.M) for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= a.rotin[a.hval[e] * Q + dec[f * N + a.col[e]]];
-                s_synd[f] = a.inv[x];
+                if (m < a.M) for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= gf_rot_in<Q>(gf, dec[f * N + a.col[e]], a.hval[e]);
+                s_synd[f] = gf.inv[x];
                 if ((x == 0 && a.early_stop)) { s_done[f] = pass + 1; atomicSub(s_alive, 1); }   /* sum_it += iter+1 */
             }
             __syncthreads();
             if (*s_alive == 0) break;
         }
         /* ---------------- results ---------------- */
-        for (int i = tid; i < nf * N; i += NT) a.out_decide[(size_t)base * N + i] = dec[i];
+        for (int i = tid; i < nf * N; i += nthr) a.out_decide[(size_t)base * N + i] = dec[i];
         if (tid < nf) {
             a.out_synd[base + tid] = s_synd[tid];
             a.out_iters[base + tid] = s_done[tid] > 0 ? s_done[tid] : a.nb_iter_max;      /* NB_LDPC.c:474 */
         }
-        __syncthreads();
     }
 }
 
@@ -341,90 +381,87 @@ __global__ void __launch_bounds__(NT, 2) decode_kernel(const KArgs a)
  * unit-boundary kernels (parity tests call these through the C ABI)
  * ---------------------------------------------------------------------------------------------- */
 template <int Q>
-__global__ void select_kernel(const float *rows, float *llr, int *gf, int B, int n_m, unsigned *slow)
+__global__ void __launch_bounds__(UNIT_NT) select_kernel(const float *rows, float *llr, int *gf, int B, int n_m, unsigned *slow)
 {
     constexpr int VPL = QTraits<Q>::VPL;
-    __shared__ WarpScratch<Q> wss[NW];
+    constexpr int UW = UNIT_NT / 32;
+    __shared__ uint32_t scr_s[UW][QTraits<Q>::SCR_WORDS + 64];     /* + slack: a lane may read one row past the sentinel */
+    __shared__ uint32_t sel_s[UW][36];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch<Q> &ws = wss[warp];
-    for (int r = blockIdx.x * NW + warp; r < B; r += gridDim.x * NW) {
-        float v[VPL];
-        load_row<Q>(rows + (size_t)r * Q, lane, v);
-        store_row<Q>(ws.row, lane, v);
-        float l; int s;
-        warp_select_nm<Q>(v, lane, ws, n_m, l, s, slow);
-        if (lane < n_m) { llr[(size_t)r * n_m + lane] = l; gf[(size_t)r * n_m + lane] = s; }
+    uint32_t *scr[1] = { scr_s[warp] };
+    uint32_t *sel[1] = { sel_s[warp] };
+    for (int r = blockIdx.x * UW + warp; r < B; r += gridDim.x * UW) {
+        float v[1][VPL];
+        load_row<Q>(rows + (size_t)r * Q, lane, v[0]);
+        float l[1]; int s[1];
+        select_edges<Q, 1>(v, lane, scr, sel, n_m, l, s, slow);
+        if (lane < n_m) { llr[(size_t)r * n_m + lane] = l[0]; gf[(size_t)r * n_m + lane] = s[0]; }
         __syncwarp();
     }
 }
 
 /* ElementaryStep on B pairs; symbols already binary images (0..q-1) with lens */
+template <int Q>
 __global__ void es_kernel(const float *in1, const float *in2, const uint8_t *s1, const uint8_t *s2, const int *len1,
-                          const int *len2, float *out, uint8_t *so, int *leno, uint32_t *maskbuf, int B, int n_m,
-                          int nb_oper, int mwords)
+                          const int *len2, float *out, uint8_t *so, int *leno, uint32_t *maskbuf, int B, int n_m, int nb_oper)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
-    leno[i] = es_serial(in1 + (size_t)i * n_m, s1 + (size_t)i * n_m, len1[i], in2 + (size_t)i * n_m, s2 + (size_t)i * n_m,
-                        len2[i], out + (size_t)i * n_m, so + (size_t)i * n_m, maskbuf + (size_t)i * mwords, 1, mwords, n_m, nb_oper);
+    leno[i] = es_serial<Q>(in1 + (size_t)i * n_m, s1 + (size_t)i * n_m, len1[i], in2 + (size_t)i * n_m, s2 + (size_t)i * n_m,
+                           len2[i], out + (size_t)i * n_m, so + (size_t)i * n_m, maskbuf + (size_t)i * 8, 1, n_m, nb_oper);
 }
 
-/* one check node (bubble ECN) for B input sets: same chain/merge/finish code as the decoder */
+/* one check node (bubble ECN) for B input sets: same tile code as the decoder, one warp per tile */
 template <int Q>
-__global__ void checknode_kernel(const KArgs a, int node, const float *vllr, const int *vgf, float *cllr, int *cgf, int B)
+__global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int node, const float *vllr, const int *vgf,
+                                                              float *cllr, int *cgf, int B)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     extern __shared__ __align__(16) unsigned char smem[];
-    Lists ls;
-    ls.llr = reinterpret_cast<float *>(smem + a.off_llr);
-    ls.sym = smem + a.off_sym;
-    ls.len = smem + a.off_len;
-    ls.L = a.L; ls.n_m = a.n_m;
-    uint32_t *masks = reinterpret_cast<uint32_t *>(smem + a.off_mask);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpScratch<Q> &ws = reinterpret_cast<WarpScratch<Q> *>(smem + a.off_ws)[warp];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    WarpMem<Q> wm(smem, a, warp);
+    const Lists &ls = wm.ls;
+    GFTab gf;
+    load_gf_tables(smem, a, gf);
+    __syncthreads();
     const int e0 = a.row_ptr[node], dc = a.row_ptr[node + 1] - e0, n_m = a.n_m;
-    const int mwords = (Q + 31) / 32;
-    for (int b0 = blockIdx.x * a.G; b0 < B; b0 += gridDim.x * a.G) {
-        const int items = min(a.G, B - b0);
-        for (int i = tid; i < items * dc * n_m; i += NT) {
-            const int item = i / (dc * n_m), r = i - item * dc * n_m, t = r / n_m, k = r - t * n_m;
-            const size_t src = ((size_t)(b0 + item) * dc + t) * n_m + k;
-            ls.l(item, t)[k] = vllr[src];
-            const int g = vgf[src];
-            ls.s(item, t)[k] = a.rotin[a.hval[e0 + t] * Q + (g & (Q - 1))];
-            if (k == 0) ls.n(item, t) = (uint8_t)n_m;
+    for (int b0 = (blockIdx.x * nw + warp) * a.cpw; b0 < B; b0 += gridDim.x * nw * a.cpw) {
+        const int cnt = min(a.cpw, B - b0);
+        for (int i = lane; i < cnt * dc * n_m; i += 32) {
+            const int c = i / (dc * n_m), r = i - c * dc * n_m, t = r / n_m, k = r - t * n_m;
+            const size_t src = ((size_t)(b0 + c) * dc + t) * n_m + k;
+            ls.l(c, t)[k] = vllr[src];
+            ls.s(c, t)[k] = (uint8_t)gf_rot_in<Q>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]);
+            if (k == 0) ls.n(c, t) = (uint8_t)n_m;
         }
-        __syncthreads();
-        for (int task = tid; task < items * 2; task += NT)
-            chain_task(ls, task >> 1, dc, task & 1, masks + (task % a.tasks), a.tasks, mwords, a.nb_oper);
-        __syncthreads();
-        for (int task = tid; task < items * (dc - 2); task += NT)
-            merge_task(ls, task / (dc - 2), dc, task % (dc - 2), masks + (task % a.tasks), a.tasks, mwords, a.nb_oper);
-        __syncthreads();
-        for (int w = warp; w < items * dc; w += NW) {
-            const int item = w / dc, t = w - item * dc, lo_id = id_out(dc, t);
-            float mcv[VPL];
-            finish_edge<Q>(ls.l(item, lo_id), ls.s(item, lo_id), ls.n(item, lo_id), a.rotout + a.hval[e0 + t] * Q, n_m,
-                           a.offset, lane, ws, nullptr, mcv);
-            float *dst = cllr + ((size_t)(b0 + item) * dc + t) * Q;
-            store_row<Q>(dst, lane, mcv);
-            int *gdst = cgf + ((size_t)(b0 + item) * dc + t) * Q;
+        if (lane < cnt) wm.meta[lane] = make_int4(e0, dc, 0, 0);
+        __syncwarp();
+        tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
+        for (int c = 0; c < cnt; c++)
+            for (int t = 0; t < dc; t++) {
+                const int lo_id = id_out(dc, t);
+                const RecView nr = finish_list<Q>(ls.l(c, lo_id), ls.s(c, lo_id), ls.n(c, lo_id), a.hval[e0 + t], gf, a.offset, lane);
+                float mcv[VPL];
+                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr[0]), mcv);
+                float *dst = cllr + ((size_t)(b0 + c) * dc + t) * Q;
+                store_row<Q>(dst, lane, mcv);
+                int *gdst = cgf + ((size_t)(b0 + c) * dc + t) * Q;
 #pragma unroll
-            for (int j = 0; j < VPL; j++) if (Q >= 32 || lane < Q) gdst[lane * VPL + j] = lane * VPL + j;   /* :276 */
-        }
-        __syncthreads();
+                for (int j = 0; j < VPL; j++) if (Q >= 32 || lane < Q) gdst[lane * VPL + j] = lane * VPL + j;   /* :276 */
+            }
+        __syncwarp();
     }
 }
 
 /* Decision + Syndrom on dense APP[B][N][q] */
 template <int Q>
-__global__ void decision_kernel(const KArgs a, const float *app, int *decide, int B)
+__global__ void __launch_bounds__(UNIT_NT) decision_kernel(const KArgs a, const float *app, int *decide, int B)
 {
     constexpr int VPL = QTraits<Q>::VPL;
+    constexpr int UW = UNIT_NT / 32;
     const int lane = threadIdx.x & 31;
     const long total = (long)B * a.N;
-    for (long r = (long)blockIdx.x * NW + (threadIdx.x >> 5); r < total; r += (long)gridDim.x * NW) {
+    for (long r = (long)blockIdx.x * UW + (threadIdx.x >> 5); r < total; r += (long)gridDim.x * UW) {
         float v[VPL];
         load_row<Q>(app + r * Q, lane, v);
         const int d = warp_argmin<Q>(v, lane);
@@ -456,16 +493,16 @@ __global__ void syndrome_kernel(const KArgs a, const int *decide, int *synd, int
 /* channel intake as a standalone kernel: dense LLR and (optionally) the sorted intrinsic arrays
  * (channel.c:66-91).  The sort is only needed for interface parity with decoder_t.intrinsic_*. */
 template <int Q>
-__global__ void channel_kernel(const KArgs a, const float *noisy, float *llr, float *illr, int *igf, int B)
+__global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const float *noisy, float *llr, float *illr, int *igf, int B)
 {
     constexpr int VPL = QTraits<Q>::VPL;
-    __shared__ WarpScratch<Q> wss[NW];
+    constexpr int UW = UNIT_NT / 32;
+    __shared__ double ts[UW][16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch<Q> &ws = wss[warp];
     const long total = (long)B * a.N;
-    for (long r = (long)blockIdx.x * NW + warp; r < total; r += (long)gridDim.x * NW) {
+    for (long r = (long)blockIdx.x * UW + warp; r < total; r += (long)gridDim.x * UW) {
         float v[VPL];
-        intake_variable<Q>(noisy + r * a.logq, a.den, a.img, lane, ws, v);
+        intake_variable<Q>(noisy + r * a.logq, a.den, a.img, lane, ts[warp], v);
         if (llr) store_row<Q>(llr + r * Q, lane, v);
         if (illr) {
             /* full stable sort = q rounds of the exact scan (channel.c:78-91) */
@@ -500,8 +537,9 @@ struct nbgpu_ctx {
     int *row_ptr_h;  /* host copies for get_state */
     int *inv_h;
     /* device buffers */
-    int *d_row_ptr, *d_col, *d_order, *d_step_ptr, *d_isolated;
-    uint8_t *d_hval, *d_last, *d_rotin, *d_rotout, *d_img, *d_inv;
+    int *d_row_ptr, *d_col, *d_step_ptr, *d_isolated;
+    uint32_t *d_cninfo, *d_einfo;
+    uint8_t *d_hval, *d_rotin, *d_rotout, *d_img, *d_inv;
     float *d_app; uint8_t *d_ctov; uint8_t *d_dec;
     float *d_in; size_t in_capacity;
     int *d_decide, *d_synd, *d_iters, *d_frame_slot, *d_slot_frame;
@@ -542,24 +580,31 @@ template <typename T> static int upload(nbgpu_ctx *c, T **dst, const std::vector
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-/* shared-memory plan for G items */
-static void plan_smem(KArgs &k, int G, size_t ws_bytes)
-{
-    k.G = G;
-    k.L = 4 * k.dc_max - 6; if (k.L < 2) k.L = 2;
-    k.tasks = G * (k.dc_max - 2 > 2 ? k.dc_max - 2 : 2);
-    int off = 0;
-    k.off_llr = off; off += G * k.L * k.n_m * 4;
-    k.off_sym = off; off += align_up(G * k.L * k.n_m, 16);
-    k.off_len = off; off += align_up(G * k.L, 16);
-    k.off_mask = off; off += align_up(((k.q + 31) / 32) * k.tasks * 4, 16);
-    k.off_ws = off; off += (int)ws_bytes * NW;
-    k.off_misc = off; off += align_up((2 + 3 * k.F) * 4, 16);
-    k.smem_bytes = off;
-}
+static int scr_words(int q) { return q == 16 ? QTraits<16>::SCR_WORDS : q == 64 ? QTraits<64>::SCR_WORDS : QTraits<256>::SCR_WORDS; }
 
-template <int Q> static size_t ws_size() { return sizeof(WarpScratch<Q>); }
-static size_t ws_size_q(int q) { return q == 16 ? ws_size<16>() : q == 64 ? ws_size<64>() : ws_size<256>(); }
+/* shared-memory plan for nw warps of cpw check nodes each (see KArgs) */
+static void plan_smem(KArgs &k, int nw, int cpw)
+{
+    k.nw = nw; k.cpw = cpw; k.cap = nw * cpw;
+    k.L = 4 * k.dc_max - 6; if (k.L < 2) k.L = 2;
+    int off = 0;
+    k.off_tab = off; off += 512;
+    k.off_misc = off; off += align_up((2 + 3 * k.F) * 4, 16);
+    /* per-warp scratch area: scr[NE] | sel[NE] | mask | meta */
+    int wa = NE * scr_words(k.q) * 4;
+    k.wa_sel = wa; wa += NE * 36 * 4;
+    k.wa_mask = wa; wa += (k.q > 64) ? 8 * 32 * 4 : 0;
+    k.wa_meta = wa; wa += cpw * 16;
+    k.wa_bytes = align_up(wa, 16);
+    k.off_wa = off; off += nw * k.wa_bytes;
+    /* per-warp lists: llr | sym | len */
+    int wb = cpw * k.L * k.n_m * 4;
+    k.wb_sym = wb; wb += align_up(cpw * k.L * k.n_m, 4);
+    k.wb_len = wb; wb += cpw * k.L;
+    k.wb_bytes = align_up(wb, 16);
+    k.off_wb = off; off += nw * k.wb_bytes;
+    k.smem_bytes = off + 256;            /* slack: select_edges may read one key row past a sentinel row */
+}
 
 extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu_params *p, int device, int max_batch)
 {
@@ -610,17 +655,25 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     c->row_ptr_h = (int *)malloc(sizeof(int) * (M + 1)); memcpy(c->row_ptr_h, code->row_ptr, sizeof(int) * (M + 1));
     c->inv_h = (int *)malloc(sizeof(int) * q); memcpy(c->inv_h, code->inv, sizeof(int) * q);
 
-    /* launch geometry: shared-memory budget -> items per step G, frames per group F, step schedule */
-    const int budget = getenv("NBGPU_SMEM_KB") ? atoi(getenv("NBGPU_SMEM_KB")) * 1024 : 100 * 1024;
+    /* launch geometry: shared-memory budget -> warps per CTA, check nodes per warp, frames per group, step schedule */
+    if (N >= (1 << 20) || E >= (1 << 24)) { ctx_err(c, "code too large for the packed graph tables (N < 2^20, E < 2^24)"); nbgpu_destroy(c); return NBGPU_EINVAL; }
+    const int budget = getenv("NBGPU_SMEM_KB") ? atoi(getenv("NBGPU_SMEM_KB")) * 1024 : 216 * 1024;
     k.F = 1;
-    int G = 64;
-    if (p->cns_per_step > 0) G = p->cns_per_step;
-    for (;; G--) { plan_smem(k, G, ws_size_q(q)); if (k.smem_bytes <= budget || G == 1) break; }
+    int nw = getenv("NBGPU_WARPS") ? atoi(getenv("NBGPU_WARPS")) : NT_MAX / 32, cpw = getenv("NBGPU_CPW") ? atoi(getenv("NBGPU_CPW")) : 8;
+    nw = std::max(1, std::min(nw, NT_MAX / 32)); cpw = std::max(1, std::min(cpw, 32));
+    if (p->cns_per_step > 0) cpw = std::max(1, std::min(cpw, (p->cns_per_step + nw - 1) / nw));
+    for (;;) {
+        plan_smem(k, nw, cpw);
+        if (k.smem_bytes <= budget) break;
+        if (nw > 8) nw -= 2; else if (cpw > 1) cpw--; else if (nw > 1) nw--; else break;
+    }
+    if (k.smem_bytes > 227 * 1024) { ctx_err(c, "decoder working set does not fit in shared memory (%d bytes for one warp)", k.smem_bytes); nbgpu_destroy(c); return NBGPU_EINVAL; }
+    const int G = k.cap;
     /* choose F: smallest number of frames per group that keeps the steps reasonably full */
     int bestF = 1; double bestU = -1;
     nbgpu_schedule sched; memset(&sched, 0, sizeof sched);
     for (int F = 1; F <= G && F <= 64; F *= 2) {
-        if (p->frames_per_cta > 0) F = p->frames_per_cta;
+        if (p->frames_per_cta > 0) F = std::min(p->frames_per_cta, G);
         nbgpu_schedule s2;
         nbgpu_build_schedule(code, G / F > 0 ? G / F : 1, &s2);
         const double util = (double)M * F / ((double)s2.nsteps * G);
@@ -630,31 +683,43 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     }
     k.F = bestF < 1 ? 1 : bestF;
     if (k.F > G) k.F = G;
-    plan_smem(k, G, ws_size_q(q));
+    plan_smem(k, nw, cpw);
     nbgpu_build_schedule(code, G / k.F > 0 ? G / k.F : 1, &sched);
     k.nsteps = sched.nsteps;
-    std::vector<int> order(sched.order, sched.order + M), step_ptr(sched.step_ptr, sched.step_ptr + sched.nsteps + 1);
+    std::vector<int> step_ptr(sched.step_ptr, sched.step_ptr + sched.nsteps + 1);
+    std::vector<uint32_t> cninfo(M), einfo(E);
+    for (int i = 0; i < M; i++) {
+        const int m = sched.order[i];
+        cninfo[i] = (uint32_t)code->row_ptr[m] | ((uint32_t)(code->row_ptr[m + 1] - code->row_ptr[m]) << 24);
+    }
+    for (int e = 0; e < E; e++) einfo[e] = (uint32_t)code->col[e] | ((uint32_t)code->val[e] << 20) | ((uint32_t)last[e] << 28);
     nbgpu_free_schedule(&sched);
     std::vector<int> row_ptr(code->row_ptr, code->row_ptr + M + 1), col(code->col, code->col + E);
     if (isolated.empty()) isolated.push_back(0), k.n_isolated = 0; else k.n_isolated = (int)isolated.size();
+    /* multiplication/division by the edge coefficient: closed exponent form when the tables have it */
+    k.gf_closed = 1;
+    for (int a2 = 0; a2 < q && k.gf_closed; a2++) for (int b2 = 1; b2 < q; b2++) {
+        const int mul = a2 ? ((a2 + b2 - 2) % (q - 1)) + 1 : 0, dv = a2 ? ((a2 - b2 + (q - 1)) % (q - 1)) + 1 : 0;
+        if (code->mulgf[a2 * q + b2] != mul || code->divgf[a2 * q + b2] != dv) { k.gf_closed = 0; break; }
+    }
+    if (getenv("NBGPU_GF_TABLES")) k.gf_closed = 0;
 
     int rc;
-    if ((rc = upload(c, &c->d_row_ptr, row_ptr)) || (rc = upload(c, &c->d_col, col)) || (rc = upload(c, &c->d_order, order)) ||
+    if ((rc = upload(c, &c->d_row_ptr, row_ptr)) || (rc = upload(c, &c->d_col, col)) || (rc = upload(c, &c->d_cninfo, cninfo)) ||
+        (rc = upload(c, &c->d_einfo, einfo)) ||
         (rc = upload(c, &c->d_step_ptr, step_ptr)) || (rc = upload(c, &c->d_isolated, isolated)) || (rc = upload(c, &c->d_hval, hval)) ||
-        (rc = upload(c, &c->d_last, last)) || (rc = upload(c, &c->d_rotin, rotin)) || (rc = upload(c, &c->d_rotout, rotout)) ||
+        (rc = upload(c, &c->d_rotin, rotin)) || (rc = upload(c, &c->d_rotout, rotout)) ||
         (rc = upload(c, &c->d_img, img)) || (rc = upload(c, &c->d_inv, inv))) { nbgpu_destroy(c); return rc; }
-    k.row_ptr = c->d_row_ptr; k.col = c->d_col; k.order = c->d_order; k.step_ptr = c->d_step_ptr; k.isolated = c->d_isolated;
-    k.hval = c->d_hval; k.last = c->d_last; k.rotin = c->d_rotin; k.rotout = c->d_rotout; k.img = c->d_img; k.inv = c->d_inv;
+    k.row_ptr = c->d_row_ptr; k.col = c->d_col; k.cninfo = c->d_cninfo; k.einfo = c->d_einfo; k.step_ptr = c->d_step_ptr; k.isolated = c->d_isolated;
+    k.hval = c->d_hval; k.rotin = c->d_rotin; k.rotout = c->d_rotout; k.img = c->d_img; k.inv = c->d_inv;
 
-    /* occupancy -> persistent grid */
+    /* persistent grid: one CTA per SM */
     const void *fn = q == 16 ? (const void *)decode_kernel<16> : q == 64 ? (const void *)decode_kernel<64> : (const void *)decode_kernel<256>;
     CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
     const void *fn2 = q == 16 ? (const void *)checknode_kernel<16> : q == 64 ? (const void *)checknode_kernel<64> : (const void *)checknode_kernel<256>;
     CK(c, cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
     int per_sm = 0;
-    if (q == 16) { CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<16>, NT, k.smem_bytes)); }
-    else if (q == 64) { CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<64>, NT, k.smem_bytes)); }
-    else { CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<256>, NT, k.smem_bytes)); }
+    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, k.nw * 32, k.smem_bytes, cudaOccupancyDefault));
     if (per_sm < 1) { ctx_err(c, "decode kernel does not fit on an SM (smem %d bytes)", k.smem_bytes); nbgpu_destroy(c); return NBGPU_ECUDA; }
     if (getenv("NBGPU_CTAS_PER_SM")) per_sm = std::min(per_sm, atoi(getenv("NBGPU_CTAS_PER_SM")));
     c->per_sm = per_sm;
@@ -687,7 +752,7 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    void *bufs[] = { c->d_row_ptr, c->d_col, c->d_order, c->d_step_ptr, c->d_isolated, c->d_hval, c->d_last, c->d_rotin,
+    void *bufs[] = { c->d_row_ptr, c->d_col, c->d_cninfo, c->d_einfo, c->d_step_ptr, c->d_isolated, c->d_hval, c->d_rotin,
                      c->d_rotout, c->d_img, c->d_inv, c->d_app, c->d_ctov, c->d_dec, c->d_in, c->d_decide, c->d_synd,
                      c->d_iters, c->d_frame_slot, c->d_slot_frame, c->d_queue };
     for (void *b : bufs) if (b) cudaFree(b);
@@ -744,9 +809,9 @@ extern "C" int nbgpu_run(nbgpu_ctx *c)
     const int groups = (k.B + k.F - 1) / k.F;
     const int grid = std::min(c->grid, groups);
     CK(c, cudaEventRecord(c->ev0, c->stream));
-    if (c->q == 16) decode_kernel<16><<<grid, NT, k.smem_bytes, c->stream>>>(k);
-    else if (c->q == 64) decode_kernel<64><<<grid, NT, k.smem_bytes, c->stream>>>(k);
-    else decode_kernel<256><<<grid, NT, k.smem_bytes, c->stream>>>(k);
+    if (c->q == 16) decode_kernel<16><<<grid, k.nw * 32, k.smem_bytes, c->stream>>>(k);
+    else if (c->q == 64) decode_kernel<64><<<grid, k.nw * 32, k.smem_bytes, c->stream>>>(k);
+    else decode_kernel<256><<<grid, k.nw * 32, k.smem_bytes, c->stream>>>(k);
     CK(c, cudaGetLastError());
     CK(c, cudaEventRecord(c->ev1, c->stream));
     c->launches += 1;
@@ -801,8 +866,8 @@ extern "C" int nbgpu_host_unregister(void *ptr)
 extern "C" int nbgpu_geometry(const nbgpu_ctx *c, int *geo)
 {
     if (!c || !geo) return NBGPU_EINVAL;
-    geo[0] = c->grid; geo[1] = c->k.F; geo[2] = c->k.G / (c->k.F > 0 ? c->k.F : 1); geo[3] = c->k.nsteps;
-    geo[4] = c->k.smem_bytes; geo[5] = c->nslots; geo[6] = c->per_sm; geo[7] = c->k.rec_stride;
+    geo[0] = c->grid; geo[1] = c->k.F; geo[2] = c->k.cap / (c->k.F > 0 ? c->k.F : 1); geo[3] = c->k.nsteps;
+    geo[4] = c->k.smem_bytes; geo[5] = c->nslots; geo[6] = c->k.nw; geo[7] = c->k.cpw;
     return NBGPU_OK;
 }
 extern "C" long nbgpu_slow_selects(nbgpu_ctx *c)
@@ -880,10 +945,10 @@ extern "C" int nbgpu_select_nm(nbgpu_ctx *c, const float *rows, float *llr, int 
     DevBuf<float> d_rows, d_llr; DevBuf<int> d_gf;
     CK(c, d_rows.alloc((size_t)B * q)); CK(c, d_llr.alloc((size_t)B * n_m)); CK(c, d_gf.alloc((size_t)B * n_m));
     CK(c, cudaMemcpyAsync(d_rows.p, rows, (size_t)B * q * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    const int grid = std::min((B + NW - 1) / NW, 148 * 8);
-    if (q == 16) select_kernel<16><<<grid, NT, 0, c->stream>>>(d_rows.p, d_llr.p, d_gf.p, B, n_m, c->d_slow);
-    else if (q == 64) select_kernel<64><<<grid, NT, 0, c->stream>>>(d_rows.p, d_llr.p, d_gf.p, B, n_m, c->d_slow);
-    else select_kernel<256><<<grid, NT, 0, c->stream>>>(d_rows.p, d_llr.p, d_gf.p, B, n_m, c->d_slow);
+    const int grid = std::min((B + UNIT_NT / 32 - 1) / (UNIT_NT / 32), 148 * 8);
+    if (q == 16) select_kernel<16><<<grid, UNIT_NT, 0, c->stream>>>(d_rows.p, d_llr.p, d_gf.p, B, n_m, c->d_slow);
+    else if (q == 64) select_kernel<64><<<grid, UNIT_NT, 0, c->stream>>>(d_rows.p, d_llr.p, d_gf.p, B, n_m, c->d_slow);
+    else select_kernel<256><<<grid, UNIT_NT, 0, c->stream>>>(d_rows.p, d_llr.p, d_gf.p, B, n_m, c->d_slow);
     CK(c, cudaGetLastError());
     c->launches++;
     CK(c, cudaMemcpyAsync(llr, d_llr.p, (size_t)B * n_m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -897,7 +962,7 @@ extern "C" int nbgpu_elementary_step(nbgpu_ctx *c, const float *in1, const float
 {
     if (!c || !in1 || !in2 || !idx1 || !idx2 || !out || !idxout || B < 1) { ctx_err(c, "nbgpu_elementary_step: bad argument"); return NBGPU_EINVAL; }
     CK(c, cudaSetDevice(c->device));
-    const int n_m = c->p.n_m, q = c->q, mwords = (q + 31) / 32;
+    const int n_m = c->p.n_m, q = c->q, mwords = 8;
     /* symbols -> binary images + valid lengths (first -1 ends a list, bubble_decoder.c:478) */
     std::vector<uint8_t> s1((size_t)B * n_m), s2((size_t)B * n_m);
     std::vector<int> l1(B), l2(B);
@@ -925,8 +990,9 @@ extern "C" int nbgpu_elementary_step(nbgpu_ctx *c, const float *in1, const float
     CK(c, cudaMemcpy(dl1.p, l1.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(dl2.p, l2.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemset(dso.p, 0, (size_t)B * n_m));
-    es_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, dmask.p, B, n_m,
-                                                     c->p.nb_oper, mwords);
+    if (q == 16) es_kernel<16><<<(B + 127) / 128, 128, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, dmask.p, B, n_m, c->p.nb_oper);
+    else if (q == 64) es_kernel<64><<<(B + 127) / 128, 128, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, dmask.p, B, n_m, c->p.nb_oper);
+    else es_kernel<256><<<(B + 127) / 128, 128, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, dmask.p, B, n_m, c->p.nb_oper);
     CK(c, cudaGetLastError());
     c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));
@@ -949,10 +1015,10 @@ extern "C" int nbgpu_check_node(nbgpu_ctx *c, int node, const float *vllr, const
     CK(c, dcl.alloc((size_t)B * dc * q)); CK(c, dcg.alloc((size_t)B * dc * q));
     CK(c, cudaMemcpy(dvl.p, vllr, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(dvg.p, vgf, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
-    const int grid = std::min((B + c->k.G - 1) / c->k.G, 148 * 4);
-    if (q == 16) checknode_kernel<16><<<grid, NT, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
-    else if (q == 64) checknode_kernel<64><<<grid, NT, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
-    else checknode_kernel<256><<<grid, NT, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
+    const int grid = std::min((B + c->k.cap - 1) / c->k.cap, 148);
+    if (q == 16) checknode_kernel<16><<<grid, c->k.nw * 32, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
+    else if (q == 64) checknode_kernel<64><<<grid, c->k.nw * 32, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
+    else checknode_kernel<256><<<grid, c->k.nw * 32, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
     CK(c, cudaGetLastError());
     c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));
@@ -969,12 +1035,12 @@ extern "C" int nbgpu_decision_syndrome(nbgpu_ctx *c, const float *app, int *deci
     DevBuf<float> dapp; DevBuf<int> ddec, dsyn;
     CK(c, dapp.alloc((size_t)B * N * q)); CK(c, ddec.alloc((size_t)B * N)); CK(c, dsyn.alloc(B));
     CK(c, cudaMemcpy(dapp.p, app, (size_t)B * N * q * 4, cudaMemcpyHostToDevice));
-    const int grid = (int)std::min<long>(((long)B * N + NW - 1) / NW, 148 * 8);
-    if (q == 16) decision_kernel<16><<<grid, NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
-    else if (q == 64) decision_kernel<64><<<grid, NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
-    else decision_kernel<256><<<grid, NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
+    const int grid = (int)std::min<long>(((long)B * N + UNIT_NT / 32 - 1) / (UNIT_NT / 32), 148 * 8);
+    if (q == 16) decision_kernel<16><<<grid, UNIT_NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
+    else if (q == 64) decision_kernel<64><<<grid, UNIT_NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
+    else decision_kernel<256><<<grid, UNIT_NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
     CK(c, cudaGetLastError());
-    syndrome_kernel<<<std::min(B, 148 * 4), NT, 0, c->stream>>>(c->k, ddec.p, dsyn.p, B);
+    syndrome_kernel<<<std::min(B, 148 * 4), UNIT_NT, 0, c->stream>>>(c->k, ddec.p, dsyn.p, B);
     CK(c, cudaGetLastError());
     c->launches += 2;
     CK(c, cudaStreamSynchronize(c->stream));
@@ -994,10 +1060,10 @@ extern "C" int nbgpu_channel_awgn_bpsk(nbgpu_ctx *c, const float *noisy, float s
     CK(c, cudaMemcpy(dn.p, noisy, (size_t)B * N * c->logq * 4, cudaMemcpyHostToDevice));
     KArgs k = c->k;
     k.den = 2.0 * (double)(float)(sigma * sigma);
-    const int grid = (int)std::min<long>(((long)B * N + NW - 1) / NW, 148 * 8);
-    if (q == 16) channel_kernel<16><<<grid, NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
-    else if (q == 64) channel_kernel<64><<<grid, NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
-    else channel_kernel<256><<<grid, NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
+    const int grid = (int)std::min<long>(((long)B * N + UNIT_NT / 32 - 1) / (UNIT_NT / 32), 148 * 8);
+    if (q == 16) channel_kernel<16><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
+    else if (q == 64) channel_kernel<64><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
+    else channel_kernel<256><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
     CK(c, cudaGetLastError());
     c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));

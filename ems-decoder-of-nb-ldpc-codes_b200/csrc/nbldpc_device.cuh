@@ -2,13 +2,16 @@
  * nbldpc_device.cuh -- device functions of the EMS decoder (sm_100a).
  *
  * Building blocks (reference lines they replace):
- *   warp_select_nm   NB_LDPC.c:354-374   stable top-n_m of q values + normalisation, one warp per edge
- *   es_serial        bubble_decoder.c:316-593  ElementaryStep, one THREAD per step (32 steps per warp)
- *   warp_argmin      tools.c:312-330     Decision
+ *   expand_record    bubble_decoder.c:262-270   dense q-vector of one stored C->V message
+ *   select_edges     NB_LDPC.c:354-374          stable top-n_m of q values + normalisation, one warp
+ *                                               per edge, NE edges interleaved for latency hiding
+ *   es_serial        bubble_decoder.c:316-593   ElementaryStep, one THREAD per step (32 per warp)
+ *   warp_argmin      tools.c:312-330            Decision
  * GF symbols travel through the check node as BINARY IMAGES so that GF addition is XOR
  * (ADDGF[a][b] == inv[img[a]^img[b]] is verified on the host); the multiplication by the edge
- * coefficient on the way in (bubble_decoder.c:133-152) and the division on the way out (:249-254) are
- * fused with the image mapping into two q x q byte tables (rotin / rotout).
+ * coefficient on the way in (bubble_decoder.c:133-152) and the division on the way out (:249-254) use
+ * the exponent form of the reference tables (MULGF[a][b] = ((a+b-2) mod (q-1))+1, verified on the
+ * host; a table fallback exists for caller-supplied tables of another shape).
  *
  * All LLR arithmetic uses the explicit round-to-nearest intrinsics (__fadd_rn/__fsub_rn): one IEEE
  * f32 operation where the reference has one, never contracted or re-associated.
@@ -24,9 +27,39 @@
 template <int Q> struct QTraits {
     static constexpr int VPL = (Q >= 32) ? Q / 32 : 1;      /* values per lane when a warp holds one row */
     static constexpr int LOGQ = (Q == 16) ? 4 : (Q == 64) ? 6 : 8;
+    static constexpr int SCR_WORDS = (VPL + 1) * 32 > Q ? (VPL + 1) * 32 : Q;   /* per-edge scratch, u32 words */
 };
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+/* GF(q) helpers shared by every kernel: byte tables in shared memory + multiplication mode */
+struct GFTab {
+    const uint8_t *img;      /* [q] symbol -> binary image (shared)            */
+    const uint8_t *inv;      /* [q] binary image -> symbol (shared)            */
+    const uint8_t *rotin;    /* [q*q] global fallback: img[MULGF[sym][h]]       */
+    const uint8_t *rotout;   /* [q*q] global fallback: DIVGF[inv[s]][h]         */
+    int closed;              /* 1: MULGF/DIVGF are the exponent closed forms    */
+};
+
+/* img[MULGF[sym][h]], bubble_decoder.c:145 */
+template <int Q> __device__ __forceinline__ int gf_rot_in(const GFTab &g, int sym, int h)
+{
+    if (g.closed) {
+        int e = sym + h - 2;
+        e = (e >= Q - 1) ? e - (Q - 1) : e;
+        return g.img[sym ? e + 1 : 0];
+    }
+    return g.rotin[h * Q + sym];
+}
+/* DIVGF[inv[s]][h], bubble_decoder.c:251 */
+template <int Q> __device__ __forceinline__ int gf_rot_out(const GFTab &g, int s, int h)
+{
+    if (g.closed) {
+        const int sym = g.inv[s];
+        int e = sym - h;
+        e = (e < 0) ? e + (Q - 1) : e;
+        return sym ? e + 1 : 0;
+    }
+    return g.rotout[h * Q + s];
+}
 
 /* ---- row I/O: a warp moves one q-float row; lane holds symbols lane*VPL .. lane*VPL+VPL-1 ---- */
 template <int Q> __device__ __forceinline__ void load_row(const float *row, int lane, float (&v)[QTraits<Q>::VPL])
@@ -53,6 +86,48 @@ template <int Q> __device__ __forceinline__ void store_row(float *row, int lane,
         if (lane < Q) row[lane] = v[0];
     }
 }
+template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, float x)
+{
+    float v[QTraits<Q>::VPL];
+#pragma unroll
+    for (int j = 0; j < QTraits<Q>::VPL; j++) v[j] = x;
+    store_row<Q>(row, lane, v);
+}
+
+/* ---- stored C->V message of one edge ("record"): llr[n_m] f32 | sat f32 | stp i32 | sym[n_m] u8 ----
+ * A dense CtoV row is "stp explicit (symbol, LLR) pairs + the constant sat everywhere else"
+ * (bubble_decoder.c:262-270), so the record is lossless. */
+struct RecView {
+    float llr; int sym; float sat; int stp;     /* llr/sym: entry 'lane' (garbage for lane >= stp) */
+};
+__device__ __forceinline__ RecView load_record(const uint8_t *rec, int n_m, int lane)
+{
+    RecView r;
+    const int k = lane < n_m ? lane : 0;
+    r.llr = reinterpret_cast<const float *>(rec)[k];
+    const int2 tail = *reinterpret_cast<const int2 *>(rec + 4 * n_m);
+    r.sat = __int_as_float(tail.x);
+    r.stp = tail.y;
+    r.sym = rec[4 * n_m + 8 + k];
+    return r;
+}
+/* dense values of this lane's symbols; scr = per-edge scratch (>= q floats), free on return */
+template <int Q>
+__device__ __forceinline__ void expand_record(const RecView &r, int lane, float *scr, float (&c)[QTraits<Q>::VPL])
+{
+    constexpr int VPL = QTraits<Q>::VPL;
+    if (r.stp == 0) {                              /* warp-uniform: first pass (CtoV = 0) */
+#pragma unroll
+        for (int j = 0; j < VPL; j++) c[j] = r.sat;
+        return;
+    }
+    fill_row<Q>(scr, lane, r.sat);
+    __syncwarp();
+    if (lane < r.stp) scr[r.sym] = r.llr;
+    __syncwarp();
+    load_row<Q>(scr, lane, c);
+    __syncwarp();
+}
 
 /* ---- in-lane sorting networks on u32 keys ---- */
 __device__ __forceinline__ void cswap(uint32_t &a, uint32_t &b)
@@ -75,13 +150,6 @@ template <int VPL> __device__ __forceinline__ void sort_keys(uint32_t (&k)[VPL])
     }
 }
 
-/* per-warp scratch in shared memory */
-template <int Q> struct WarpScratch {
-    uint32_t sorted[(QTraits<Q>::VPL + 1) * 32];   /* lane-sorted keys, [r][lane]; row VPL = +inf      */
-    float row[Q < 64 ? 64 : Q];                    /* one dense q-row (also 2*logq doubles at intake) */
-    uint32_t sel[36];                              /* winners of the selection rounds                  */
-};
-
 /* lexicographic (value, symbol) minimum across the warp with the reference's scan semantics:
  * strict '<' from the +1e5 sentinel, ties -> lowest symbol; "nothing below 1e5" -> (1e5, BIG). */
 __device__ __forceinline__ void warp_lexmin(float &bv, int &bg)
@@ -94,127 +162,183 @@ __device__ __forceinline__ void warp_lexmin(float &bv, int &bg)
     }
 }
 
-/* Decision for one row held by a warp (tools.c:317-329) */
+/* Decision for one row held by a warp (tools.c:317-329): argmin with strict '<' from 1e5, ties ->
+ * lowest symbol, default 0.  For non-negative finite rows (the normal case) the float bit pattern is
+ * monotone, so one integer REDUX finds the minimum and a ballot the lowest lane holding it. */
 template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTraits<Q>::VPL], int lane)
 {
     constexpr int VPL = QTraits<Q>::VPL;
+    const bool active = (Q >= 32) || lane < Q;
+    uint32_t mb = NB_KEY_INF, ob = 0;
+#pragma unroll
+    for (int j = 0; j < VPL; j++) { const uint32_t b = __float_as_uint(v[j]); mb = min(mb, b); ob |= b; }
+    if (!active) { mb = NB_KEY_INF; ob = 0; }
+    if (!__any_sync(NB_FULL, ob >= 0x7f800000u)) {
+        const uint32_t m = __reduce_min_sync(NB_FULL, mb);
+        if (!(__uint_as_float(m) < NB_SENT)) return 0;
+        const unsigned who = __ballot_sync(NB_FULL, mb == m);
+        int j0 = VPL - 1;
+#pragma unroll
+        for (int j = VPL - 2; j >= 0; j--) if (__float_as_uint(v[j]) == m) j0 = j;
+        const int src = __ffs(who) - 1;
+        return src * VPL + __shfl_sync(NB_FULL, j0, src);
+    }
     float bv = NB_SENT; int bg = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < VPL; j++) if ((Q >= 32 || lane < Q) && v[j] < bv) { bv = v[j]; bg = lane * VPL + j; }
+    for (int j = 0; j < VPL; j++) if (active && v[j] < bv) { bv = v[j]; bg = lane * VPL + j; }
     warp_lexmin(bv, bg);
     return (bg == 0x7fffffff) ? 0 : bg;
 }
 
 /*
- * Truncation of one V->C message (NB_LDPC.c:354-374): the n_m smallest of the q values mvc[], in
- * ascending order, ties -> lowest symbol, values >= 1e5 never selected (slot keeps (1e5, symbol 0) and
- * symbol 0 is masked), then LLR[k] -= LLR[0], LLR[0] = 0.
+ * Truncation of V->C messages (NB_LDPC.c:354-374) for NE edges at once: the n_m smallest of the q
+ * values mvc[e][], ascending, ties -> lowest symbol, values >= 1e5 never selected (slot keeps
+ * (1e5, symbol 0) and symbol 0 is masked), then LLR[k] -= LLR[0], LLR[0] = 0.
  *
- * Fast path: every value is turned into a UNIQUE 32-bit key  (f32 bits & ~(q-1)) | symbol.  For
- * non-negative finite floats the bit pattern is monotone in the value, so key order == (value, symbol)
- * order except when two values differ only in the log2(q) dropped mantissa bits.  Each lane sorts its
- * VPL keys with a register network and parks them in shared memory; n_m+1 rounds of one REDUX.MIN
- * over the lane heads then pop the global minimum, the owning lane advancing its head pointer.  The
- * result is accepted only if (a) no value was negative/NaN/Inf, (b) all adjacent winners (including
- * the (n_m+1)-th) differ in their kept bits, (c) the n_m winners are < 1e5.  Otherwise the warp
- * re-runs the exact scan (slow path, same semantics as the reference loop).
+ * Fast path: every value becomes a UNIQUE 32-bit key (f32 bits & ~(q-1)) | symbol.  For non-negative
+ * finite floats the bit pattern is monotone in the value, so key order == (value, symbol) order except
+ * when two values differ only in the log2(q) dropped mantissa bits.  Each lane sorts its VPL keys with
+ * a register network and parks them in shared memory ([rank][lane], row VPL = +inf); n_m+1 rounds of
+ * one REDUX.MIN over the lane heads pop the global minimum, the owning lane fetching its next key.
+ * The NE independent REDUX chains are interleaved so that their latencies overlap.  A result is
+ * accepted only if (a) no value was negative/NaN/Inf, (b) adjacent winners (including the
+ * (n_m+1)-th) differ in their kept bits, (c) the n_m winners are < 1e5.  Otherwise that edge re-runs
+ * the exact scan (same semantics as the reference loop).
  *
- * Result: lane k < n_m returns (llr, sym) = k-th entry.  mvc row must already be in ws.row.
+ * scr[e]: SCR_WORDS u32 of warp-private scratch (free on entry, free on return); sel[e]: 36 u32.
+ * Result: lane k < n_m holds (out_llr[e], out_sym[e]) = k-th entry of edge e.
  */
-template <int Q>
-__device__ __forceinline__ void warp_select_nm(const float (&mvc)[QTraits<Q>::VPL], int lane, WarpScratch<Q> &ws,
-                                               int n_m, float &out_llr, int &out_sym, unsigned *slow_counter)
+template <int Q, int NE>
+__device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::VPL], int lane, uint32_t *(&scr)[NE],
+                                             uint32_t *(&sel)[NE], int n_m, float (&out_llr)[NE], int (&out_sym)[NE],
+                                             unsigned *slow_counter)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     constexpr int LOGQ = QTraits<Q>::LOGQ;
     const bool active = (Q >= 32) || lane < Q;
-    uint32_t key[VPL];
-    bool bad = false;
+    const int rounds = (n_m + 1 < Q) ? n_m + 1 : Q;
+    uint32_t head[NE];
+    const uint32_t *nxt[NE];
+    bool bad[NE];
 #pragma unroll
-    for (int j = 0; j < VPL; j++) {
-        const uint32_t b = __float_as_uint(mvc[j]);
-        bad |= active && (b >= 0x7f800000u);
-        key[j] = active ? ((b & ~uint32_t(Q - 1)) | uint32_t(lane * VPL + j)) : NB_KEY_INF;
+    for (int e = 0; e < NE; e++) {
+        uint32_t key[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; j++) {
+            const uint32_t b = __float_as_uint(mvc[e][j]);
+            key[j] = active ? ((b & ~uint32_t(Q - 1)) | uint32_t(lane * VPL + j)) : NB_KEY_INF;
+        }
+        sort_keys<VPL>(key);
+        bad[e] = active && key[VPL - 1] >= 0x7f800000u;
+#pragma unroll
+        for (int j = 1; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
+        scr[e][VPL * 32 + lane] = NB_KEY_INF;
+        head[e] = key[0];
+        nxt[e] = scr[e] + 32 + lane;
     }
-    sort_keys<VPL>(key);
+    /* no __syncwarp needed: every lane only reads back what it wrote itself */
+    for (int r = 0; r < rounds; r++) {
 #pragma unroll
-    for (int j = 0; j < VPL; j++) ws.sorted[j * 32 + lane] = key[j];
-    ws.sorted[VPL * 32 + lane] = NB_KEY_INF;
-    uint32_t head = key[0];
-    int p = 0;
-    for (int r = 0; r <= n_m; r++) {
-        const uint32_t m = __reduce_min_sync(NB_FULL, head);
-        if (head == m) {
-            ws.sel[r] = m;
-            p = min(p + 1, VPL);
-            head = ws.sorted[p * 32 + lane];
+        for (int e = 0; e < NE; e++) {
+            const uint32_t m = __reduce_min_sync(NB_FULL, head[e]);
+            if (head[e] == m) {
+                sel[e][r] = m;
+                head[e] = *nxt[e];
+                nxt[e] += 32;
+            }
         }
     }
     __syncwarp();
-    const uint32_t mine = ws.sel[min(lane, n_m)];
-    const uint32_t nxt = ws.sel[min(lane + 1, n_m)];
-    const bool amb = lane < n_m && ((mine >> LOGQ) == (nxt >> LOGQ));
-    int sym = int(mine & uint32_t(Q - 1));
-    float val = ws.row[sym];
-    const bool over = lane < n_m && !(val < NB_SENT);
-    if (__any_sync(NB_FULL, bad || amb || over)) {
-        /* exact scan, NB_LDPC.c:356-369 */
-        if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
-        float tmp[VPL];
 #pragma unroll
-        for (int j = 0; j < VPL; j++) tmp[j] = mvc[j];
-        for (int k = 0; k < n_m; k++) {
-            float bv = NB_SENT; int bg = 0x7fffffff;
+    for (int e = 0; e < NE; e++) store_row<Q>(reinterpret_cast<float *>(scr[e]), lane, mvc[e]);
+    __syncwarp();
 #pragma unroll
-            for (int j = 0; j < VPL; j++) if (active && tmp[j] < bv) { bv = tmp[j]; bg = lane * VPL + j; }
-            warp_lexmin(bv, bg);
-            if (bg == 0x7fffffff) bg = 0;                      /* nothing below 1e5: (1e5, symbol 0) */
+    for (int e = 0; e < NE; e++) {
+        const uint32_t mine = sel[e][min(lane, rounds - 1)];
+        const uint32_t after = sel[e][min(lane + 1, rounds - 1)];
+        const bool amb = lane < n_m && lane + 1 < rounds && ((mine >> LOGQ) == (after >> LOGQ));
+        int sym = int(mine & uint32_t(Q - 1));
+        float val = reinterpret_cast<const float *>(scr[e])[sym];
+        const bool over = lane < n_m && !(val < NB_SENT);
+        if (__any_sync(NB_FULL, bad[e] || amb || over)) {
+            /* exact scan, NB_LDPC.c:356-369 */
+            if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
+            float tmp[VPL];
 #pragma unroll
-            for (int j = 0; j < VPL; j++) if (bg == lane * VPL + j) tmp[j] = NB_SENT;   /* NB_LDPC.c:368 */
-            if (lane == k) { val = bv; sym = bg; }
+            for (int j = 0; j < VPL; j++) tmp[j] = mvc[e][j];
+            for (int k = 0; k < n_m; k++) {
+                float bv = NB_SENT; int bg = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < VPL; j++) if (active && tmp[j] < bv) { bv = tmp[j]; bg = lane * VPL + j; }
+                warp_lexmin(bv, bg);
+                if (bg == 0x7fffffff) bg = 0;                      /* nothing below 1e5: (1e5, symbol 0) */
+#pragma unroll
+                for (int j = 0; j < VPL; j++) if (bg == lane * VPL + j) tmp[j] = NB_SENT;   /* NB_LDPC.c:368 */
+                if (lane == k) { val = bv; sym = bg; }
+            }
         }
+        const float v0 = __shfl_sync(NB_FULL, val, 0);
+        out_llr[e] = (lane == 0) ? 0.0f : __fsub_rn(val, v0);                               /* NB_LDPC.c:372-373 */
+        out_sym[e] = sym;
     }
-    const float v0 = __shfl_sync(NB_FULL, val, 0);
-    out_llr = (lane == 0) ? 0.0f : __fsub_rn(val, v0);                                  /* NB_LDPC.c:372-373 */
-    out_sym = sym;
+    __syncwarp();
 }
 
 /*
  * ElementaryStep (bubble_decoder.c:316-593), one thread per step.
  * Lists are (llr[n_m], sym[n_m], len): entries >= len are "absent" (reference: LLR 1e5, symbol -1);
  * their LLR slot holds 1e5 so that sums with them are >= 1e5 exactly as in tab_aux.
- * Symbols are binary images: ADDGF == XOR.  mask = q/32 words at stride mstride (shared memory).
+ * Symbols are binary images: ADDGF == XOR.  The "already output" set is a q-bit mask: registers for
+ * q <= 64, q/32 words at stride mstride in shared memory for q = 256.
  * Eight bubbles (nb_bubble = 8, :327): p < 4 walks row p to the right, p >= 4 walks column p-4 down
  * from row 4 (:445-460, :548-555).  Pop = first strictly smallest candidate below 1e5, else bubble 0
  * (minimum(), :38-56).
  */
+template <int Q>
 __device__ __forceinline__ int es_serial(const float *__restrict__ l1, const uint8_t *__restrict__ s1, int len1,
                                          const float *__restrict__ l2, const uint8_t *__restrict__ s2, int len2,
                                          float *__restrict__ lo, uint8_t *__restrict__ so,
-                                         uint32_t *mask, int mstride, int mwords, int n_m, int nb_oper)
+                                         uint32_t *mask, int mstride, int n_m, int nb_oper)
 {
     float bv[8];
-    for (int w = 0; w < mwords; w++) mask[w * mstride] = 0u;
-    const float a0 = l1[0], a1 = l1[1], a2 = l1[2], a3 = l1[3], a4 = l1[4];
-    bv[0] = __fadd_rn(a0, l2[0]); bv[1] = __fadd_rn(a1, l2[0]); bv[2] = __fadd_rn(a2, l2[0]); bv[3] = __fadd_rn(a3, l2[0]);
-    bv[4] = __fadd_rn(a4, l2[0]); bv[5] = __fadd_rn(a4, l2[1]); bv[6] = __fadd_rn(a4, l2[2]); bv[7] = __fadd_rn(a4, l2[3]);
+    unsigned long long seen = 0ull;
+    if constexpr (Q > 64) {
+#pragma unroll
+        for (int w = 0; w < Q / 32; w++) mask[w * mstride] = 0u;
+    }
+    const float a4 = l1[4], b0 = l2[0];
+    bv[0] = __fadd_rn(l1[0], b0); bv[1] = __fadd_rn(l1[1], b0); bv[2] = __fadd_rn(l1[2], b0); bv[3] = __fadd_rn(l1[3], b0);
+    bv[4] = __fadd_rn(a4, b0); bv[5] = __fadd_rn(a4, l2[1]); bv[6] = __fadd_rn(a4, l2[2]); bv[7] = __fadd_rn(a4, l2[3]);
     /* walk coordinate of each bubble, 8 bits each: column j for p<4 (starts 0), row i for p>=4 (starts 4) */
     unsigned long long pos = 0x0404040400000000ull;
     int s = 0;
     for (int ss = 0; ss < nb_oper; ss++) {
-        float best = NB_SENT; int bp = 0;
-#pragma unroll
-        for (int p = 0; p < 8; p++) if (bv[p] < best) { best = bv[p]; bp = p; }
-        const float val = (best < NB_SENT) ? best : bv[0];
+        /* 8-way strict minimum, ties -> lowest bubble (tree of "right < left") */
+        const bool c01 = bv[1] < bv[0], c23 = bv[3] < bv[2], c45 = bv[5] < bv[4], c67 = bv[7] < bv[6];
+        const float m01 = c01 ? bv[1] : bv[0], m23 = c23 ? bv[3] : bv[2], m45 = c45 ? bv[5] : bv[4], m67 = c67 ? bv[7] : bv[6];
+        const int i01 = c01 ? 1 : 0, i23 = c23 ? 3 : 2, i45 = c45 ? 5 : 4, i67 = c67 ? 7 : 6;
+        const bool c03 = m23 < m01, c47 = m67 < m45;
+        const float m03 = c03 ? m23 : m01, m47 = c47 ? m67 : m45;
+        const int i03 = c03 ? i23 : i01, i47 = c47 ? i67 : i45;
+        const bool c07 = m47 < m03;
+        float val = c07 ? m47 : m03;
+        int bp = c07 ? i47 : i03;
+        if (!(val < NB_SENT)) { bp = 0; val = bv[0]; }
         const int c = int((pos >> (8 * bp)) & 0xffull);
         const int i = (bp < 4) ? bp : c;
         const int j = (bp < 4) ? c : bp - 4;
         if (i >= len1 || j >= len2) break;                                  /* :478-484 */
         const int g = s1[i] ^ s2[j];                                        /* :486 */
-        const uint32_t w = mask[(g >> 5) * mstride], bit = 1u << (g & 31);
-        if (!(w & bit)) {                                                   /* :490-496 */
-            lo[s] = val; so[s] = (uint8_t)g; mask[(g >> 5) * mstride] = w | bit; s++;
+        bool fresh;
+        if constexpr (Q > 64) {
+            const uint32_t w = mask[(g >> 5) * mstride], bit = 1u << (g & 31);
+            fresh = !(w & bit);
+            if (fresh) mask[(g >> 5) * mstride] = w | bit;
+        } else {
+            fresh = !((seen >> g) & 1ull);
+            seen |= 1ull << g;
         }
+        if (fresh) { lo[s] = val; so[s] = (uint8_t)g; s++; }                /* :490-496 */
         if (s == n_m) break;                                                /* :502 */
         if (i >= n_m - 1 || j >= n_m - 1) break;                            /* :506-544 */
         pos += 1ull << (8 * bp);                                            /* :548-555 */

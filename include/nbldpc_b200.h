@@ -90,8 +90,8 @@ typedef struct {
     /* syndrome_ems only (NB_LDPC.c:189-201, all commented out there) */
     int   d1, d2, d3, cfg_trunc, n_cv, border;
     /* tuning; 0 = automatic */
-    int   frames_per_cta;
-    int   cns_per_step;
+    int   frames_per_cta;  /* frames decoded together by one CTA                                  */
+    int   cns_per_step;    /* upper bound on the check nodes (over all frames of a CTA) per step  */
 } nbgpu_params;
 
 typedef struct nbgpu_ctx nbgpu_ctx;
@@ -134,8 +134,8 @@ int nbgpu_timer_end(nbgpu_ctx *ctx, float *ms);
 /* page-lock / unlock a caller-owned host buffer so that the H2D/D2H copies of nbgpu_decode_* are DMA copies */
 int nbgpu_host_register(void *ptr, size_t bytes);
 int nbgpu_host_unregister(void *ptr);
-/* geometry chosen by nbgpu_create: geo[8] = grid (CTAs), frames per CTA group, check nodes per step,
- * steps per pass, dynamic shared memory bytes, resident frame slots, CTAs per SM, record stride */
+/* geometry chosen by nbgpu_create: geo[8] = grid (CTAs), frames per CTA group, check nodes per step and frame,
+ * steps per pass, dynamic shared memory bytes, resident frame slots, warps per CTA, check nodes per warp */
 int nbgpu_geometry(const nbgpu_ctx *ctx, int *geo);
 /* selection rows that needed the exact (slow) scan since creation; diagnostic */
 long nbgpu_slow_selects(nbgpu_ctx *ctx);
