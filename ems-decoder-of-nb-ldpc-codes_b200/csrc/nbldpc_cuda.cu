@@ -57,16 +57,17 @@ struct KArgs {
     /* shared memory map (bytes): tables | misc | per-warp scratch areas | per-warp lists */
     int off_tab, off_misc, off_wa, wa_bytes, off_wb, wb_bytes;
     int wa_sel, wa_mask, wa_meta;       /* offsets inside a warp's scratch area (scr at 0) */
-    int wb_sym, wb_len;                 /* offsets inside a warp's list area (llr at 0) */
+    int lstride;                        /* bytes per list: n_m f32 | n_m u8 | len u8 | pad */
     int smem_bytes;
 };
 
-/* list addressing inside a warp's shared memory; c = check node of the warp's tile */
+/* Lists of a warp's tile in shared memory, by 32-bit shared-window address.  c = check node of the
+ * tile, li = list id.  One list = n_m f32 LLRs, n_m u8 symbols (binary images), 1 u8 length. */
 struct Lists {
-    float *llr; uint8_t *sym; uint8_t *len; int L, n_m;
-    __device__ __forceinline__ float *l(int c, int li) const { return llr + (c * L + li) * n_m; }
-    __device__ __forceinline__ uint8_t *s(int c, int li) const { return sym + (c * L + li) * n_m; }
-    __device__ __forceinline__ uint8_t &n(int c, int li) const { return len[c * L + li]; }
+    uint32_t base; int lstride, cstride, n_m;
+    __device__ __forceinline__ uint32_t at(int c, int li) const { return base + c * cstride + li * lstride; }
+    __device__ __forceinline__ uint32_t sym(uint32_t list) const { return list + 4 * n_m; }
+    __device__ __forceinline__ uint32_t len(uint32_t list) const { return list + 5 * n_m; }
 };
 /* list ids of one node with degree dc: U[t] = t; F after s steps = dc+s-1 (s>=1); B after s steps =
  * dc+(dc-2)+s-1; merge k = dc+2(dc-2)+k  (bubble_decoder.c:166-227: MatriceInter rows) */
@@ -85,7 +86,7 @@ __device__ __forceinline__ int id_out(int dc, int t)
 template <int Q> struct WarpMem {
     uint32_t *scr[NE];       /* per in-flight edge: sorted keys / dense row               */
     uint32_t *sel[NE];       /* winners of the selection rounds                            */
-    uint32_t *mask;          /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided  */
+    uint32_t mask;           /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided (shared address) */
     int4 *meta;              /* [cpw] {first edge, degree (0 = skip), frame, -}            */
     Lists ls;
     __device__ __forceinline__ WarpMem(unsigned char *smem, const KArgs &a, int warp)
@@ -96,13 +97,10 @@ template <int Q> struct WarpMem {
             scr[e] = reinterpret_cast<uint32_t *>(wa) + e * QTraits<Q>::SCR_WORDS;
             sel[e] = reinterpret_cast<uint32_t *>(wa + a.wa_sel) + e * 36;
         }
-        mask = reinterpret_cast<uint32_t *>(wa + a.wa_mask);
+        mask = smem_u32(wa + a.wa_mask);
         meta = reinterpret_cast<int4 *>(wa + a.wa_meta);
-        unsigned char *wb = smem + a.off_wb + warp * a.wb_bytes;
-        ls.llr = reinterpret_cast<float *>(wb);
-        ls.sym = wb + a.wb_sym;
-        ls.len = wb + a.wb_len;
-        ls.L = a.L; ls.n_m = a.n_m;
+        ls.base = smem_u32(smem + a.off_wb + warp * a.wb_bytes);
+        ls.lstride = a.lstride; ls.cstride = a.L * a.lstride; ls.n_m = a.n_m;
     }
 };
 
@@ -111,7 +109,7 @@ template <int Q> struct WarpMem {
  * Slots 2/3: the merges ES(F_k, B_{dc-3-k}) (:217-227) whose later input appears in round r-1:
  * k = r-1 (if k >= dc-3-k) and k = dc-2-r (if dc-3-k = r-1 > k). */
 template <int Q>
-__device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const int4 *meta, int cnt, int dcmax, uint32_t *mask,
+__device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const int4 *meta, int cnt, int dcmax, uint32_t mask,
                                                       int lane, int nb_oper)
 {
     for (int r = 1; r <= dcmax - 2; r++) {
@@ -128,9 +126,12 @@ __device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const int
                     valid = (slot == 2) ? (k <= dc - 3 && 2 * k >= dc - 3) : (k >= 0 && k <= dc - 3 && r - 1 > k);
                     a = id_F(dc, k); b = id_B(dc, dc - 3 - k); o = id_M(dc, k);
                 }
-                if (valid)
-                    ls.n(c, o) = (uint8_t)es_serial<Q>(ls.l(c, a), ls.s(c, a), ls.n(c, a), ls.l(c, b), ls.s(c, b), ls.n(c, b),
-                                                       ls.l(c, o), ls.s(c, o), mask + lane, 32, ls.n_m, nb_oper);
+                if (valid) {
+                    const uint32_t la = ls.at(c, a), lb = ls.at(c, b), lo = ls.at(c, o);
+                    const int s = es_serial<Q>(la, ls.sym(la), (int)lds_u8(ls.len(la)), lb, ls.sym(lb), (int)lds_u8(ls.len(lb)),
+                                               lo, ls.sym(lo), mask + 4 * lane, ls.n_m, nb_oper);
+                    sts_u8(ls.len(lo), (uint32_t)s);
+                }
             }
             __syncwarp();
         }
@@ -139,14 +140,17 @@ __device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const int
 
 /* phase 3 core: from the check node's output list of one edge (binary-image symbols) build the
  * record entry of this lane and the saturation constant (bubble_decoder.c:231-264). */
-template <int Q>
-__device__ __forceinline__ RecView finish_list(const float *lo, const uint8_t *so, int len, int h, const GFTab &gf,
-                                               float offset, int lane)
+template <int Q, bool CLOSED>
+__device__ __forceinline__ RecView finish_list(const Lists &ls, uint32_t list, int h, const GFTab &gf, float offset, int lane)
 {
     RecView r;
+    const int len = (int)lds_u8(ls.len(list));
     r.stp = len;                                                     /* first absent entry, :233-243 */
     r.llr = NB_SENT; r.sym = 0;
-    if (lane < len) { r.llr = lo[lane]; r.sym = gf_rot_out<Q>(gf, so[lane], h); }   /* DIVGF by the coefficient, :249-254 */
+    if (lane < len) {
+        r.llr = lds_f32(list + 4 * lane);
+        r.sym = gf_rot_out<Q, CLOSED>(gf, (int)lds_u8(ls.sym(list) + lane), h);       /* DIVGF by the coefficient, :249-254 */
+    }
     const float last = __shfl_sync(NB_FULL, r.llr, max(len - 1, 0));
     r.sat = __fadd_rn(len > 0 ? last : NB_SENT, offset);             /* :264 (len == 0 cannot occur) */
     return r;
@@ -192,10 +196,27 @@ __device__ __forceinline__ void load_gf_tables(unsigned char *smem, const KArgs 
 {
     uint8_t *tab = smem + a.off_tab;
     for (int i = threadIdx.x; i < a.q; i += blockDim.x) { tab[i] = a.img[i]; tab[256 + i] = a.inv[i]; }
-    gf.img = tab; gf.inv = tab + 256; gf.rotin = a.rotin; gf.rotout = a.rotout; gf.closed = a.gf_closed;
+    gf.img = tab; gf.inv = tab + 256; gf.rotin = a.rotin; gf.rotout = a.rotout;
 }
 
+/* L2 prefetch of the APP rows and CtoV records of up to NE consecutive edges (one instruction) */
 template <int Q>
+__device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t *ctov_f, const uint32_t *einfo, int ed, int n,
+                                               int rec_stride, int lane)
+{
+    constexpr int LPR = (Q * 4 + 127) / 128;               /* 128-byte lines per row */
+    const char *p = nullptr;
+    if (lane < NE * LPR) {
+        const int e = lane / LPR;
+        if (e < n) p = reinterpret_cast<const char *>(app_f + (size_t)(einfo[ed + e] & 0xfffff) * Q) + (lane % LPR) * 128;
+    } else if (lane < NE * LPR + 3) {
+        const int off = (lane - NE * LPR) * 128;
+        if (off < n * rec_stride) p = reinterpret_cast<const char *>(ctov_f + (size_t)ed * rec_stride) + off;
+    }
+    if (p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+template <int Q, bool CLOSED>
 __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
 {
     constexpr int VPL = QTraits<Q>::VPL;
@@ -211,10 +232,10 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
     int *s_done = misc + 2;             /* [F]  0 = iterating, else iters value to report */
     int *s_badrow = misc + 2 + a.F;     /* [F]  first check row with non-zero syndrome */
     int *s_synd = misc + 2 + 2 * a.F;   /* [F]  last syndrome value */
-    const int F = a.F, N = a.N, n_m = a.n_m, dcm = a.dc_max;
-    const size_t slot_app = (size_t)F * N * Q;
-    float *app = a.app + blockIdx.x * slot_app;
-    uint8_t *ctov = a.ctov + (size_t)blockIdx.x * F * a.E * a.rec_stride;
+    const int F = a.F, N = a.N, n_m = a.n_m, dcm = a.dc_max, rs = a.rec_stride;
+    const size_t frame_app = (size_t)N * Q, frame_ctov = (size_t)a.E * rs;
+    float *app = a.app + blockIdx.x * F * frame_app;
+    uint8_t *ctov = a.ctov + blockIdx.x * F * frame_ctov;
     uint8_t *dec = a.dec + (size_t)blockIdx.x * F * N;
 
     for (;;) {
@@ -234,7 +255,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
             store_row<Q>(app + ((size_t)f * N + n) * Q, lane, v);
         }
         for (int i = tid; i < nf * a.E; i += nthr)           /* CtoV = 0: stp 0, constant 0.0f */
-            *reinterpret_cast<int2 *>(ctov + (size_t)i * a.rec_stride + 4 * n_m) = make_int2(0, 0);
+            *reinterpret_cast<int2 *>(ctov + (size_t)i * rs + 4 * n_m) = make_int2(0, 0);
         for (int i = tid; i < F; i += nthr) { s_done[i] = (i < nf) ? 0 : -1; s_synd[i] = 0; }
         if (tid == 0) { *s_alive = nf; for (int f = 0; f < nf; f++) { a.frame_slot[base + f] = blockIdx.x * F + f; a.slot_frame[blockIdx.x * F + f] = base + f; } }
         __syncthreads();
@@ -254,49 +275,58 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
                 const int per = (items + nw - 1) / nw;        /* <= cpw by construction of the schedule */
                 const int first = warp * per;
                 const int cnt = max(0, min(per, items - first));
+                /* tile description: one lane per check node */
+                if (lane < cnt) {
+                    const int item = first + lane, f = item / ncn;
+                    const uint32_t info = a.cninfo[c0 + item - f * ncn];
+                    wm.meta[lane] = make_int4(info & 0xffffff, s_done[f] ? 0 : (int)(info >> 24), f, 0);
+                }
+                __syncwarp();
                 /* ---------------- phase 1 ---------------- */
-                {
-                    int f = cnt > 0 ? first / ncn : 0, ci = first - f * ncn;
-                    for (int c = 0; c < cnt; c++) {
-                        const uint32_t info = a.cninfo[c0 + ci];
-                        const int e0 = info & 0xffffff;
-                        const int dc = s_done[f] ? 0 : (int)(info >> 24);
-                        if (lane == 0) wm.meta[c] = make_int4(e0, dc, f, 0);
-                        for (int t = 0; t < dc; t += NE) {
-                            float v[NE][VPL];
-                            RecView r[NE];
-                            int hv[NE];
+                for (int c = 0; c < cnt; c++) {
+                    const int4 mt = wm.meta[c];
+                    const int e0 = mt.x, dc = mt.y;
+                    const float *app_f = app + mt.z * frame_app;
+                    const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
+                    if (c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
+                    for (int t = 0; t < dc; t += NE) {
+                        float v[NE][VPL];
+                        RecView r[NE];
+                        int hv[NE];
 #pragma unroll
-                            for (int e = 0; e < NE; e++) {
-                                const bool valid = t + e < dc;
-                                const int ed = e0 + min(t + e, dc - 1);
-                                const uint32_t ei = a.einfo[ed];
-                                hv[e] = (ei >> 20) & 0xff;
-                                load_row<Q>(app + ((size_t)f * N + (ei & 0xfffff)) * Q, lane, v[e]);
-                                r[e] = load_record(ctov + ((size_t)f * a.E + ed) * a.rec_stride, n_m, lane);
-                                if (!valid) r[e].stp = 0;     /* duplicate of the previous edge: result ignored */
-                            }
+                        for (int e = 0; e < NE; e++) {
+                            const int ed = e0 + min(t + e, dc - 1);        /* t+e >= dc: duplicate of the last edge, result ignored */
+                            const uint32_t ei = a.einfo[ed];
+                            hv[e] = (ei >> 20) & 0xff;
+                            load_row<Q>(app_f + (size_t)(ei & 0xfffff) * Q, lane, v[e]);
+                            r[e] = load_record(ctov_f + (size_t)ed * rs, n_m, lane);
+                        }
+                        /* next pair of edges of the tile -> L2 while this pair is processed */
+                        if (t + NE < dc) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0 + t + NE, min(NE, dc - t - NE), rs, lane);
+                        else if (c + 1 < cnt) {
+                            const int4 nx = wm.meta[c + 1];
+                            if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
+                        }
 #pragma unroll
-                            for (int e = 0; e < NE; e++) {
-                                float cv[VPL];
-                                expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
+                        for (int e = 0; e < NE; e++) {
+                            float cv[VPL];
+                            expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
 #pragma unroll
-                                for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
-                            }
-                            float llr[NE]; int sym[NE];
-                            select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
+                            for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
+                        }
+                        float llr[NE]; int sym[NE];
+                        select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
 #pragma unroll
-                            for (int e = 0; e < NE; e++) {
-                                if (t + e < dc) {
-                                    if (lane < n_m) {
-                                        ls.l(c, t + e)[lane] = llr[e];
-                                        ls.s(c, t + e)[lane] = (uint8_t)gf_rot_in<Q>(gf, sym[e], hv[e]);   /* bubble_decoder.c:145 */
-                                    }
-                                    if (lane == 0) ls.n(c, t + e) = (uint8_t)n_m;
+                        for (int e = 0; e < NE; e++) {
+                            if (t + e < dc) {
+                                const uint32_t list = ls.at(c, t + e);
+                                if (lane < n_m) {
+                                    sts_f32(list + 4 * lane, llr[e]);
+                                    sts_u8(ls.sym(list) + lane, (uint32_t)gf_rot_in<Q, CLOSED>(gf, sym[e], hv[e]));   /* bubble_decoder.c:145 */
                                 }
+                                if (lane == 0) sts_u8(ls.len(list), (uint32_t)n_m);
                             }
                         }
-                        if (++ci == ncn) { ci = 0; f++; }
                     }
                 }
                 __syncwarp();
@@ -305,7 +335,10 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
                 /* ---------------- phase 3 ---------------- */
                 for (int c = 0; c < cnt; c++) {
                     const int4 mt = wm.meta[c];
-                    const int e0 = mt.x, dc = mt.y, f = mt.z;
+                    const int e0 = mt.x, dc = mt.y;
+                    float *app_f = app + mt.z * frame_app;
+                    uint8_t *ctov_f = ctov + mt.z * frame_ctov;
+                    uint8_t *dec_f = dec + mt.z * N;
                     for (int t = 0; t < dc; t += NE) {
                         float v[NE][VPL];
                         RecView r[NE];
@@ -314,8 +347,8 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
                         for (int e = 0; e < NE; e++) {
                             const int ed = e0 + min(t + e, dc - 1);
                             ei[e] = a.einfo[ed];
-                            load_row<Q>(app + ((size_t)f * N + (ei[e] & 0xfffff)) * Q, lane, v[e]);
-                            r[e] = load_record(ctov + ((size_t)f * a.E + ed) * a.rec_stride, n_m, lane);
+                            load_row<Q>(app_f + (size_t)(ei[e] & 0xfffff) * Q, lane, v[e]);
+                            r[e] = load_record(ctov_f + (size_t)ed * rs, n_m, lane);
                         }
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
@@ -328,18 +361,17 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
                             if (t + e < dc) {
-                                const int ed = e0 + t + e, var = ei[e] & 0xfffff, lo_id = id_out(dc, t + e);
-                                const RecView nr = finish_list<Q>(ls.l(c, lo_id), ls.s(c, lo_id), ls.n(c, lo_id), (ei[e] >> 20) & 0xff,
-                                                                  gf, a.offset, lane);
-                                store_record(ctov + ((size_t)f * a.E + ed) * a.rec_stride, nr, n_m, lane);
+                                const int ed = e0 + t + e, var = ei[e] & 0xfffff;
+                                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t + e)), (ei[e] >> 20) & 0xff, gf, a.offset, lane);
+                                store_record(ctov_f + (size_t)ed * rs, nr, n_m, lane);
                                 float mcv[VPL];
                                 expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr[e]), mcv);     /* :262-281 */
 #pragma unroll
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
-                                store_row<Q>(app + ((size_t)f * N + var) * Q, lane, v[e]);
+                                store_row<Q>(app_f + (size_t)var * Q, lane, v[e]);
                                 if (ei[e] >> 28) {                                                     /* tools.c:312 fused */
                                     const int d = warp_argmin<Q>(v[e], lane);
-                                    if (lane == 0) dec[f * N + var] = (uint8_t)d;
+                                    if (lane == 0) dec_f[var] = (uint8_t)d;
                                 }
                             }
                         }
@@ -354,14 +386,14 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
                 const int f = i / a.M, m = i - f * a.M;
                 if (s_done[f]) continue;
                 int x = 0;
-                for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= gf_rot_in<Q>(gf, dec[f * N + a.col[e]], a.hval[e]);
+                for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= gf_rot_in<Q, CLOSED>(gf, dec[f * N + a.col[e]], a.hval[e]);
                 if (x) atomicMin(&s_badrow[f], m);
             }
             __syncthreads();
             if (tid < nf && !s_done[tid]) {
                 const int f = tid, m = s_badrow[f];
                 int x = 0;
-                if (m < a.M) for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= gf_rot_in<Q>(gf, dec[f * N + a.col[e]], a.hval[e]);
+                if (m < a.M) for (int e = a.row_ptr[m]; e < a.row_ptr[m + 1]; e++) x ^= gf_rot_in<Q, CLOSED>(gf, dec[f * N + a.col[e]], a.hval[e]);
                 s_synd[f] = gf.inv[x];
                 if ((x == 0 && a.early_stop)) { s_done[f] = pass + 1; atomicSub(s_alive, 1); }   /* sum_it += iter+1 */
             }
@@ -400,19 +432,32 @@ __global__ void __launch_bounds__(UNIT_NT) select_kernel(const float *rows, floa
     }
 }
 
-/* ElementaryStep on B pairs; symbols already binary images (0..q-1) with lens */
+/* ElementaryStep on B pairs; symbols already binary images (0..q-1) with lens.  One thread per step;
+ * the lists are staged in shared memory because es_serial works on shared-window addresses. */
+#define ES_NT 64
 template <int Q>
-__global__ void es_kernel(const float *in1, const float *in2, const uint8_t *s1, const uint8_t *s2, const int *len1,
-                          const int *len2, float *out, uint8_t *so, int *leno, uint32_t *maskbuf, int B, int n_m, int nb_oper)
+__global__ void __launch_bounds__(ES_NT) es_kernel(const float *in1, const float *in2, const uint8_t *s1, const uint8_t *s2, const int *len1,
+                                                   const int *len2, float *out, uint8_t *so, int *leno, int B, int n_m, int nb_oper)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float fl[ES_NT][3][32];
+    __shared__ uint8_t sy[ES_NT][3][32];
+    __shared__ uint32_t mk[8][ES_NT];
+    const int t = threadIdx.x, i = blockIdx.x * ES_NT + t;
     if (i >= B) return;
-    leno[i] = es_serial<Q>(in1 + (size_t)i * n_m, s1 + (size_t)i * n_m, len1[i], in2 + (size_t)i * n_m, s2 + (size_t)i * n_m,
-                           len2[i], out + (size_t)i * n_m, so + (size_t)i * n_m, maskbuf + (size_t)i * 8, 1, n_m, nb_oper);
+    for (int k = 0; k < n_m; k++) {
+        fl[t][0][k] = in1[(size_t)i * n_m + k]; fl[t][1][k] = in2[(size_t)i * n_m + k];
+        sy[t][0][k] = s1[(size_t)i * n_m + k]; sy[t][1][k] = s2[(size_t)i * n_m + k];
+    }
+    /* mask words of one thread must be 128 bytes apart: [w][32 threads] inside this thread's half */
+    const uint32_t mask = smem_u32(&mk[0][0]) + (t >> 5) * 8 * 128 + (t & 31) * 4;
+    const int s = es_serial<Q>(smem_u32(fl[t][0]), smem_u32(sy[t][0]), len1[i], smem_u32(fl[t][1]), smem_u32(sy[t][1]), len2[i],
+                               smem_u32(fl[t][2]), smem_u32(sy[t][2]), mask, n_m, nb_oper);
+    leno[i] = s;
+    for (int k = 0; k < n_m; k++) { out[(size_t)i * n_m + k] = fl[t][2][k]; so[(size_t)i * n_m + k] = k < s ? sy[t][2][k] : 0; }
 }
 
 /* one check node (bubble ECN) for B input sets: same tile code as the decoder, one warp per tile */
-template <int Q>
+template <int Q, bool CLOSED>
 __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int node, const float *vllr, const int *vgf,
                                                               float *cllr, int *cgf, int B)
 {
@@ -430,17 +475,17 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
         for (int i = lane; i < cnt * dc * n_m; i += 32) {
             const int c = i / (dc * n_m), r = i - c * dc * n_m, t = r / n_m, k = r - t * n_m;
             const size_t src = ((size_t)(b0 + c) * dc + t) * n_m + k;
-            ls.l(c, t)[k] = vllr[src];
-            ls.s(c, t)[k] = (uint8_t)gf_rot_in<Q>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]);
-            if (k == 0) ls.n(c, t) = (uint8_t)n_m;
+            const uint32_t list = ls.at(c, t);
+            sts_f32(list + 4 * k, vllr[src]);
+            sts_u8(ls.sym(list) + k, (uint32_t)gf_rot_in<Q, CLOSED>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]));
+            if (k == 0) sts_u8(ls.len(list), (uint32_t)n_m);
         }
         if (lane < cnt) wm.meta[lane] = make_int4(e0, dc, 0, 0);
         __syncwarp();
         tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
         for (int c = 0; c < cnt; c++)
             for (int t = 0; t < dc; t++) {
-                const int lo_id = id_out(dc, t);
-                const RecView nr = finish_list<Q>(ls.l(c, lo_id), ls.s(c, lo_id), ls.n(c, lo_id), a.hval[e0 + t], gf, a.offset, lane);
+                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t)), a.hval[e0 + t], gf, a.offset, lane);
                 float mcv[VPL];
                 expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr[0]), mcv);
                 float *dst = cllr + ((size_t)(b0 + c) * dc + t) * Q;
@@ -522,6 +567,17 @@ __global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const f
     }
 }
 
+static const void *decode_fn(int q, int closed)
+{
+    if (closed) return q == 16 ? (const void *)decode_kernel<16, true> : q == 64 ? (const void *)decode_kernel<64, true> : (const void *)decode_kernel<256, true>;
+    return q == 16 ? (const void *)decode_kernel<16, false> : q == 64 ? (const void *)decode_kernel<64, false> : (const void *)decode_kernel<256, false>;
+}
+static const void *checknode_fn(int q, int closed)
+{
+    if (closed) return q == 16 ? (const void *)checknode_kernel<16, true> : q == 64 ? (const void *)checknode_kernel<64, true> : (const void *)checknode_kernel<256, true>;
+    return q == 16 ? (const void *)checknode_kernel<16, false> : q == 64 ? (const void *)checknode_kernel<64, false> : (const void *)checknode_kernel<256, false>;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * context
  * ---------------------------------------------------------------------------------------------- */
@@ -597,11 +653,9 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     k.wa_meta = wa; wa += cpw * 16;
     k.wa_bytes = align_up(wa, 16);
     k.off_wa = off; off += nw * k.wa_bytes;
-    /* per-warp lists: llr | sym | len */
-    int wb = cpw * k.L * k.n_m * 4;
-    k.wb_sym = wb; wb += align_up(cpw * k.L * k.n_m, 4);
-    k.wb_len = wb; wb += cpw * k.L;
-    k.wb_bytes = align_up(wb, 16);
+    /* per-warp lists: cpw nodes x L lists x {n_m f32 | n_m u8 | len u8} */
+    k.lstride = align_up(5 * k.n_m + 1, 4);
+    k.wb_bytes = align_up(cpw * k.L * k.lstride, 16);
     k.off_wb = off; off += nw * k.wb_bytes;
     k.smem_bytes = off + 256;            /* slack: select_edges may read one key row past a sentinel row */
 }
@@ -714,9 +768,9 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     k.hval = c->d_hval; k.rotin = c->d_rotin; k.rotout = c->d_rotout; k.img = c->d_img; k.inv = c->d_inv;
 
     /* persistent grid: one CTA per SM */
-    const void *fn = q == 16 ? (const void *)decode_kernel<16> : q == 64 ? (const void *)decode_kernel<64> : (const void *)decode_kernel<256>;
+    const void *fn = decode_fn(q, k.gf_closed);
     CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
-    const void *fn2 = q == 16 ? (const void *)checknode_kernel<16> : q == 64 ? (const void *)checknode_kernel<64> : (const void *)checknode_kernel<256>;
+    const void *fn2 = checknode_fn(q, k.gf_closed);
     CK(c, cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
     int per_sm = 0;
     CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, k.nw * 32, k.smem_bytes, cudaOccupancyDefault));
@@ -729,7 +783,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     c->nslots = c->grid * k.F;
 
     CK(c, cudaMalloc((void **)&c->d_app, (size_t)c->nslots * N * q * sizeof(float)));
-    CK(c, cudaMalloc((void **)&c->d_ctov, (size_t)c->nslots * E * k.rec_stride));
+    CK(c, cudaMalloc((void **)&c->d_ctov, (size_t)c->nslots * E * k.rec_stride + 512));
     CK(c, cudaMalloc((void **)&c->d_dec, (size_t)c->nslots * N));
     CK(c, cudaMemset(c->d_dec, 0, (size_t)c->nslots * N));
     CK(c, cudaMalloc((void **)&c->d_decide, (size_t)max_batch * N * sizeof(int)));
@@ -809,9 +863,10 @@ extern "C" int nbgpu_run(nbgpu_ctx *c)
     const int groups = (k.B + k.F - 1) / k.F;
     const int grid = std::min(c->grid, groups);
     CK(c, cudaEventRecord(c->ev0, c->stream));
-    if (c->q == 16) decode_kernel<16><<<grid, k.nw * 32, k.smem_bytes, c->stream>>>(k);
-    else if (c->q == 64) decode_kernel<64><<<grid, k.nw * 32, k.smem_bytes, c->stream>>>(k);
-    else decode_kernel<256><<<grid, k.nw * 32, k.smem_bytes, c->stream>>>(k);
+    {
+        void *args[] = { (void *)&k };
+        CK(c, cudaLaunchKernel(decode_fn(c->q, k.gf_closed), dim3(grid), dim3(k.nw * 32), args, k.smem_bytes, c->stream));
+    }
     CK(c, cudaGetLastError());
     CK(c, cudaEventRecord(c->ev1, c->stream));
     c->launches += 1;
@@ -962,7 +1017,7 @@ extern "C" int nbgpu_elementary_step(nbgpu_ctx *c, const float *in1, const float
 {
     if (!c || !in1 || !in2 || !idx1 || !idx2 || !out || !idxout || B < 1) { ctx_err(c, "nbgpu_elementary_step: bad argument"); return NBGPU_EINVAL; }
     CK(c, cudaSetDevice(c->device));
-    const int n_m = c->p.n_m, q = c->q, mwords = 8;
+    const int n_m = c->p.n_m, q = c->q;
     /* symbols -> binary images + valid lengths (first -1 ends a list, bubble_decoder.c:478) */
     std::vector<uint8_t> s1((size_t)B * n_m), s2((size_t)B * n_m);
     std::vector<int> l1(B), l2(B);
@@ -979,10 +1034,10 @@ extern "C" int nbgpu_elementary_step(nbgpu_ctx *c, const float *in1, const float
             s2[(size_t)b * n_m + k] = (y >= 0 && y < q) ? img[y] : 0;
         }
     }
-    DevBuf<float> d1, d2, dout; DevBuf<uint8_t> ds1, ds2, dso; DevBuf<int> dl1, dl2, dlo; DevBuf<uint32_t> dmask;
+    DevBuf<float> d1, d2, dout; DevBuf<uint8_t> ds1, ds2, dso; DevBuf<int> dl1, dl2, dlo;
     CK(c, d1.alloc((size_t)B * n_m)); CK(c, d2.alloc((size_t)B * n_m)); CK(c, dout.alloc((size_t)B * n_m));
     CK(c, ds1.alloc((size_t)B * n_m)); CK(c, ds2.alloc((size_t)B * n_m)); CK(c, dso.alloc((size_t)B * n_m));
-    CK(c, dl1.alloc(B)); CK(c, dl2.alloc(B)); CK(c, dlo.alloc(B)); CK(c, dmask.alloc((size_t)B * mwords));
+    CK(c, dl1.alloc(B)); CK(c, dl2.alloc(B)); CK(c, dlo.alloc(B));
     CK(c, cudaMemcpy(d1.p, in1, (size_t)B * n_m * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(d2.p, in2, (size_t)B * n_m * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(ds1.p, s1.data(), (size_t)B * n_m, cudaMemcpyHostToDevice));
@@ -990,9 +1045,10 @@ extern "C" int nbgpu_elementary_step(nbgpu_ctx *c, const float *in1, const float
     CK(c, cudaMemcpy(dl1.p, l1.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(dl2.p, l2.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemset(dso.p, 0, (size_t)B * n_m));
-    if (q == 16) es_kernel<16><<<(B + 127) / 128, 128, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, dmask.p, B, n_m, c->p.nb_oper);
-    else if (q == 64) es_kernel<64><<<(B + 127) / 128, 128, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, dmask.p, B, n_m, c->p.nb_oper);
-    else es_kernel<256><<<(B + 127) / 128, 128, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, dmask.p, B, n_m, c->p.nb_oper);
+    const int esg = (B + ES_NT - 1) / ES_NT;
+    if (q == 16) es_kernel<16><<<esg, ES_NT, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, B, n_m, c->p.nb_oper);
+    else if (q == 64) es_kernel<64><<<esg, ES_NT, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, B, n_m, c->p.nb_oper);
+    else es_kernel<256><<<esg, ES_NT, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, B, n_m, c->p.nb_oper);
     CK(c, cudaGetLastError());
     c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));
@@ -1016,9 +1072,11 @@ extern "C" int nbgpu_check_node(nbgpu_ctx *c, int node, const float *vllr, const
     CK(c, cudaMemcpy(dvl.p, vllr, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(dvg.p, vgf, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
     const int grid = std::min((B + c->k.cap - 1) / c->k.cap, 148);
-    if (q == 16) checknode_kernel<16><<<grid, c->k.nw * 32, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
-    else if (q == 64) checknode_kernel<64><<<grid, c->k.nw * 32, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
-    else checknode_kernel<256><<<grid, c->k.nw * 32, c->k.smem_bytes, c->stream>>>(c->k, node, dvl.p, dvg.p, dcl.p, dcg.p, B);
+    {
+        const float *a1 = dvl.p; const int *a2 = dvg.p; float *a3 = dcl.p; int *a4 = dcg.p;
+        void *args[] = { (void *)&c->k, (void *)&node, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&B };
+        CK(c, cudaLaunchKernel(checknode_fn(q, c->k.gf_closed), dim3(grid), dim3(c->k.nw * 32), args, c->k.smem_bytes, c->stream));
+    }
     CK(c, cudaGetLastError());
     c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));

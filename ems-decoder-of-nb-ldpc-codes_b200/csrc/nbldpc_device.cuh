@@ -30,35 +30,36 @@ template <int Q> struct QTraits {
     static constexpr int SCR_WORDS = (VPL + 1) * 32 > Q ? (VPL + 1) * 32 : Q;   /* per-edge scratch, u32 words */
 };
 
-/* GF(q) helpers shared by every kernel: byte tables in shared memory + multiplication mode */
+/* GF(q) helpers shared by every kernel: byte tables in shared memory (+ global fallback tables) */
 struct GFTab {
     const uint8_t *img;      /* [q] symbol -> binary image (shared)            */
     const uint8_t *inv;      /* [q] binary image -> symbol (shared)            */
     const uint8_t *rotin;    /* [q*q] global fallback: img[MULGF[sym][h]]       */
     const uint8_t *rotout;   /* [q*q] global fallback: DIVGF[inv[s]][h]         */
-    int closed;              /* 1: MULGF/DIVGF are the exponent closed forms    */
 };
 
-/* img[MULGF[sym][h]], bubble_decoder.c:145 */
-template <int Q> __device__ __forceinline__ int gf_rot_in(const GFTab &g, int sym, int h)
+/* img[MULGF[sym][h]], bubble_decoder.c:145.  CLOSED: MULGF[a][b] = ((a+b-2) mod (q-1))+1 (checked on the host) */
+template <int Q, bool CLOSED> __device__ __forceinline__ int gf_rot_in(const GFTab &g, int sym, int h)
 {
-    if (g.closed) {
+    if constexpr (CLOSED) {
         int e = sym + h - 2;
         e = (e >= Q - 1) ? e - (Q - 1) : e;
         return g.img[sym ? e + 1 : 0];
+    } else {
+        return g.rotin[h * Q + sym];
     }
-    return g.rotin[h * Q + sym];
 }
 /* DIVGF[inv[s]][h], bubble_decoder.c:251 */
-template <int Q> __device__ __forceinline__ int gf_rot_out(const GFTab &g, int s, int h)
+template <int Q, bool CLOSED> __device__ __forceinline__ int gf_rot_out(const GFTab &g, int s, int h)
 {
-    if (g.closed) {
+    if constexpr (CLOSED) {
         const int sym = g.inv[s];
         int e = sym - h;
         e = (e < 0) ? e + (Q - 1) : e;
         return sym ? e + 1 : 0;
+    } else {
+        return g.rotout[h * Q + s];
     }
-    return g.rotout[h * Q + s];
 }
 
 /* ---- row I/O: a warp moves one q-float row; lane holds symbols lane*VPL .. lane*VPL+VPL-1 ---- */
@@ -190,6 +191,15 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
     return (bg == 0x7fffffff) ? 0 : bg;
 }
 
+/* ---- explicit shared-window accesses (32-bit addresses: no generic-pointer arithmetic in hot loops) ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 /*
  * Truncation of V->C messages (NB_LDPC.c:354-374) for NE edges at once: the n_m smallest of the q
  * values mvc[e][], ascending, ties -> lowest symbol, values >= 1e5 never selected (slot keeps
@@ -199,11 +209,12 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
  * finite floats the bit pattern is monotone in the value, so key order == (value, symbol) order except
  * when two values differ only in the log2(q) dropped mantissa bits.  Each lane sorts its VPL keys with
  * a register network and parks them in shared memory ([rank][lane], row VPL = +inf); n_m+1 rounds of
- * one REDUX.MIN over the lane heads pop the global minimum, the owning lane fetching its next key.
- * The NE independent REDUX chains are interleaved so that their latencies overlap.  A result is
- * accepted only if (a) no value was negative/NaN/Inf, (b) adjacent winners (including the
- * (n_m+1)-th) differ in their kept bits, (c) the n_m winners are < 1e5.  Otherwise that edge re-runs
- * the exact scan (same semantics as the reference loop).
+ * one REDUX.MIN over the lane heads pop the global minimum, the owning lane fetching its next key
+ * (5 instructions per round: redux, setp, predicated st/ld/add).  The NE independent REDUX chains are
+ * interleaved so that their latencies overlap.  A result is accepted only if (a) no value was
+ * negative/NaN/Inf, (b) adjacent winners (including the (n_m+1)-th) differ in their kept bits, (c) the
+ * n_m winners are < 1e5.  Otherwise that edge re-runs the exact scan (same semantics as the reference
+ * loop).
  *
  * scr[e]: SCR_WORDS u32 of warp-private scratch (free on entry, free on return); sel[e]: 36 u32.
  * Result: lane k < n_m holds (out_llr[e], out_sym[e]) = k-th entry of edge e.
@@ -217,8 +228,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
     constexpr int LOGQ = QTraits<Q>::LOGQ;
     const bool active = (Q >= 32) || lane < Q;
     const int rounds = (n_m + 1 < Q) ? n_m + 1 : Q;
-    uint32_t head[NE];
-    const uint32_t *nxt[NE];
+    uint32_t head[NE], nxt[NE], selp[NE];
     bool bad[NE];
 #pragma unroll
     for (int e = 0; e < NE; e++) {
@@ -234,19 +244,37 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         for (int j = 1; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
         scr[e][VPL * 32 + lane] = NB_KEY_INF;
         head[e] = key[0];
-        nxt[e] = scr[e] + 32 + lane;
+        nxt[e] = smem_u32(scr[e] + 32 + lane);
+        selp[e] = smem_u32(sel[e]);
     }
     /* no __syncwarp needed: every lane only reads back what it wrote itself */
-    for (int r = 0; r < rounds; r++) {
+#define NB_SEL_ROUND(E, OFF)                                                                                   \
+    asm volatile("{\n\t"                                                                                        \
+                 ".reg .pred p;\n\t"                                                                            \
+                 ".reg .u32 m;\n\t"                                                                             \
+                 "redux.sync.min.u32 m, %0, 0xffffffff;\n\t"                                                    \
+                 "setp.eq.u32 p, %0, m;\n\t"                                                                    \
+                 "@p st.shared.u32 [%2+" #OFF "], %0;\n\t"                                                      \
+                 "@p ld.shared.u32 %0, [%1];\n\t"                                                               \
+                 "@p add.u32 %1, %1, 128;\n\t"                                                                  \
+                 "}"                                                                                             \
+                 : "+r"(head[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
+    int r = 0;
+    for (; r + 4 <= rounds; r += 4) {
 #pragma unroll
-        for (int e = 0; e < NE; e++) {
-            const uint32_t m = __reduce_min_sync(NB_FULL, head[e]);
-            if (head[e] == m) {
-                sel[e][r] = m;
-                head[e] = *nxt[e];
-                nxt[e] += 32;
-            }
-        }
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
+#pragma unroll
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 4);
+#pragma unroll
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 8);
+#pragma unroll
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 12);
+#pragma unroll
+        for (int e = 0; e < NE; e++) selp[e] += 16;
+    }
+    for (; r < rounds; r++) {
+#pragma unroll
+        for (int e = 0; e < NE; e++) { NB_SEL_ROUND(e, 0); selp[e] += 4; }
     }
     __syncwarp();
 #pragma unroll
@@ -285,32 +313,36 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
 }
 
 /*
- * ElementaryStep (bubble_decoder.c:316-593), one thread per step.
- * Lists are (llr[n_m], sym[n_m], len): entries >= len are "absent" (reference: LLR 1e5, symbol -1);
- * their LLR slot holds 1e5 so that sums with them are >= 1e5 exactly as in tab_aux.
- * Symbols are binary images: ADDGF == XOR.  The "already output" set is a q-bit mask: registers for
- * q <= 64, q/32 words at stride mstride in shared memory for q = 256.
+ * ElementaryStep (bubble_decoder.c:316-593), one thread per step; all lists live in shared memory and
+ * are addressed by 32-bit shared-window addresses.
+ * A list is n_m f32 LLRs at 'l', n_m u8 symbols at 's', and a length: entries >= len are "absent"
+ * (reference: LLR 1e5, symbol -1); their LLR slot holds 1e5 so that sums with them are >= 1e5 exactly
+ * as in tab_aux.  Symbols are binary images: ADDGF == XOR.  The "already output" set is a q-bit mask:
+ * registers for q <= 64, q/32 words 128 bytes apart in shared memory for q = 256.
  * Eight bubbles (nb_bubble = 8, :327): p < 4 walks row p to the right, p >= 4 walks column p-4 down
  * from row 4 (:445-460, :548-555).  Pop = first strictly smallest candidate below 1e5, else bubble 0
  * (minimum(), :38-56).
  */
+#define NB_BV_UPDATE(P) asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %2, " #P ";\n\tselp.f32 %0, %1, %0, q;\n\t}" : "+f"(bv[P]) : "f"(nv), "r"(bp))
 template <int Q>
-__device__ __forceinline__ int es_serial(const float *__restrict__ l1, const uint8_t *__restrict__ s1, int len1,
-                                         const float *__restrict__ l2, const uint8_t *__restrict__ s2, int len2,
-                                         float *__restrict__ lo, uint8_t *__restrict__ so,
-                                         uint32_t *mask, int mstride, int n_m, int nb_oper)
+__device__ __forceinline__ int es_serial(uint32_t l1, uint32_t s1, int len1, uint32_t l2, uint32_t s2, int len2,
+                                         uint32_t lo, uint32_t so, uint32_t mask, int n_m, int nb_oper)
 {
     float bv[8];
     unsigned long long seen = 0ull;
     if constexpr (Q > 64) {
 #pragma unroll
-        for (int w = 0; w < Q / 32; w++) mask[w * mstride] = 0u;
+        for (int w = 0; w < Q / 32; w++) sts_u32(mask + w * 128, 0u);
     }
-    const float a4 = l1[4], b0 = l2[0];
-    bv[0] = __fadd_rn(l1[0], b0); bv[1] = __fadd_rn(l1[1], b0); bv[2] = __fadd_rn(l1[2], b0); bv[3] = __fadd_rn(l1[3], b0);
-    bv[4] = __fadd_rn(a4, b0); bv[5] = __fadd_rn(a4, l2[1]); bv[6] = __fadd_rn(a4, l2[2]); bv[7] = __fadd_rn(a4, l2[3]);
+    {
+        const float a4 = lds_f32(l1 + 16), b0 = lds_f32(l2);
+        bv[0] = __fadd_rn(lds_f32(l1), b0); bv[1] = __fadd_rn(lds_f32(l1 + 4), b0);
+        bv[2] = __fadd_rn(lds_f32(l1 + 8), b0); bv[3] = __fadd_rn(lds_f32(l1 + 12), b0);
+        bv[4] = __fadd_rn(a4, b0); bv[5] = __fadd_rn(a4, lds_f32(l2 + 4));
+        bv[6] = __fadd_rn(a4, lds_f32(l2 + 8)); bv[7] = __fadd_rn(a4, lds_f32(l2 + 12));
+    }
     /* walk coordinate of each bubble, 8 bits each: column j for p<4 (starts 0), row i for p>=4 (starts 4) */
-    unsigned long long pos = 0x0404040400000000ull;
+    uint32_t posr = 0u, posc = 0x04040404u;
     int s = 0;
     for (int ss = 0; ss < nb_oper; ss++) {
         /* 8-way strict minimum, ties -> lowest bubble (tree of "right < left") */
@@ -324,30 +356,35 @@ __device__ __forceinline__ int es_serial(const float *__restrict__ l1, const uin
         float val = c07 ? m47 : m03;
         int bp = c07 ? i47 : i03;
         if (!(val < NB_SENT)) { bp = 0; val = bv[0]; }
-        const int c = int((pos >> (8 * bp)) & 0xffull);
-        const int i = (bp < 4) ? bp : c;
-        const int j = (bp < 4) ? c : bp - 4;
+        const bool isrow = bp < 4;
+        const uint32_t sh = 8u * (bp & 3);
+        const int c = int(((isrow ? posr : posc) >> sh) & 0xffu);
+        const int i = isrow ? bp : c;
+        const int j = isrow ? c : bp - 4;
         if (i >= len1 || j >= len2) break;                                  /* :478-484 */
-        const int g = s1[i] ^ s2[j];                                        /* :486 */
+        const uint32_t g = lds_u8(s1 + i) ^ lds_u8(s2 + j);                 /* :486 */
         bool fresh;
         if constexpr (Q > 64) {
-            const uint32_t w = mask[(g >> 5) * mstride], bit = 1u << (g & 31);
+            const uint32_t wa = mask + (g >> 5) * 128;
+            const uint32_t w = lds_u32(wa), bit = 1u << (g & 31);
             fresh = !(w & bit);
-            if (fresh) mask[(g >> 5) * mstride] = w | bit;
+            if (fresh) sts_u32(wa, w | bit);
         } else {
             fresh = !((seen >> g) & 1ull);
             seen |= 1ull << g;
         }
-        if (fresh) { lo[s] = val; so[s] = (uint8_t)g; s++; }                /* :490-496 */
+        if (fresh) { sts_f32(lo + 4 * s, val); sts_u8(so + s, g); s++; }     /* :490-496 */
         if (s == n_m) break;                                                /* :502 */
         if (i >= n_m - 1 || j >= n_m - 1) break;                            /* :506-544 */
-        pos += 1ull << (8 * bp);                                            /* :548-555 */
-        const int ni = (bp < 4) ? bp : c + 1;
-        const int nj = (bp < 4) ? c + 1 : bp - 4;
-        const float nv = __fadd_rn(l1[ni], l2[nj]);                         /* :557 */
-#pragma unroll
-        for (int p = 0; p < 8; p++) if (p == bp) bv[p] = nv;
+        const uint32_t inc = 1u << sh;                                      /* :548-555 */
+        posr += isrow ? inc : 0u;
+        posc += isrow ? 0u : inc;
+        const int ni = isrow ? i : i + 1;
+        const int nj = isrow ? j + 1 : j;
+        const float nv = __fadd_rn(lds_f32(l1 + 4 * ni), lds_f32(l2 + 4 * nj));   /* :557 */
+        NB_BV_UPDATE(0); NB_BV_UPDATE(1); NB_BV_UPDATE(2); NB_BV_UPDATE(3);
+        NB_BV_UPDATE(4); NB_BV_UPDATE(5); NB_BV_UPDATE(6); NB_BV_UPDATE(7);
     }
-    for (int k = s; k < n_m; k++) lo[k] = NB_SENT;                          /* :370-374 */
+    for (int k = s; k < n_m; k++) sts_f32(lo + 4 * k, NB_SENT);             /* :370-374 */
     return s;
 }
