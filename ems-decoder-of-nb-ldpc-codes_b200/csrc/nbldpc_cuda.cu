@@ -31,7 +31,12 @@
 #include <algorithm>
 #include <vector>
 
-#define NT_MAX 512        /* threads per CTA (upper bound; the plan may use fewer warps) */
+#ifndef NT_MAX
+#define NT_MAX 384        /* threads per CTA (upper bound; the plan may use fewer warps) */
+#endif
+#ifndef CTAS_PER_SM
+#define CTAS_PER_SM 2      /* resident CTAs per SM the decode kernel is compiled for (register cap 65536 / (NT_MAX * CTAS_PER_SM)) */
+#endif
 #define NE 2              /* edges interleaved per warp in phases 1 and 3 */
 #define UNIT_NT 256       /* block size of the small unit-boundary kernels */
 
@@ -155,12 +160,6 @@ __device__ __forceinline__ RecView finish_list(const Lists &ls, uint32_t list, i
     r.sat = __fadd_rn(len > 0 ? last : NB_SENT, offset);             /* :264 (len == 0 cannot occur) */
     return r;
 }
-__device__ __forceinline__ void store_record(uint8_t *rec, const RecView &r, int n_m, int lane)
-{
-    if (lane < n_m) { reinterpret_cast<float *>(rec)[lane] = r.llr; rec[4 * n_m + 8 + lane] = (uint8_t)r.sym; }
-    if (lane == 0) *reinterpret_cast<int2 *>(rec + 4 * n_m) = make_int2(__float_as_int(r.sat), r.stp);
-}
-
 /* LLR intake for one variable (channel.c:66-76), one warp: lanes < 2*logq first build the per-bit
  * terms (double)((y-s)^2) / (2 sigma^2), then every lane accumulates its symbols bit by bit with the
  * reference's float <- double + double rounding. */
@@ -217,7 +216,7 @@ __device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t
 }
 
 template <int Q, bool CLOSED>
-__global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
+__global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs a)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -234,6 +233,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
     int *s_synd = misc + 2 + 2 * a.F;   /* [F]  last syndrome value */
     const int F = a.F, N = a.N, n_m = a.n_m, dcm = a.dc_max, rs = a.rec_stride;
     const size_t frame_app = (size_t)N * Q, frame_ctov = (size_t)a.E * rs;
+    const RecLane rl(n_m, lane, rs);
     float *app = a.app + blockIdx.x * F * frame_app;
     uint8_t *ctov = a.ctov + blockIdx.x * F * frame_ctov;
     uint8_t *dec = a.dec + (size_t)blockIdx.x * F * N;
@@ -295,11 +295,11 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
                         int hv[NE];
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
-                            const int ed = e0 + min(t + e, dc - 1);        /* t+e >= dc: duplicate of the last edge, result ignored */
+                            const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));   /* t+e >= dc: duplicate of the last edge, result ignored */
                             const uint32_t ei = a.einfo[ed];
                             hv[e] = (ei >> 20) & 0xff;
-                            load_row<Q>(app_f + (size_t)(ei & 0xfffff) * Q, lane, v[e]);
-                            r[e] = load_record(ctov_f + (size_t)ed * rs, n_m, lane);
+                            load_row<Q>(app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q), lane, v[e]);
+                            r[e] = load_record(ctov_f, ed, rl);
                         }
                         /* next pair of edges of the tile -> L2 while this pair is processed */
                         if (t + NE < dc) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0 + t + NE, min(NE, dc - t - NE), rs, lane);
@@ -345,10 +345,10 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
                         uint32_t ei[NE];
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
-                            const int ed = e0 + min(t + e, dc - 1);
+                            const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));
                             ei[e] = a.einfo[ed];
-                            load_row<Q>(app_f + (size_t)(ei[e] & 0xfffff) * Q, lane, v[e]);
-                            r[e] = load_record(ctov_f + (size_t)ed * rs, n_m, lane);
+                            load_row<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e]);
+                            r[e] = load_record(ctov_f, ed, rl);
                         }
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
@@ -361,14 +361,14 @@ __global__ void __launch_bounds__(NT_MAX, 1) decode_kernel(const KArgs a)
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
                             if (t + e < dc) {
-                                const int ed = e0 + t + e, var = ei[e] & 0xfffff;
+                                const uint32_t ed = (uint32_t)(e0 + t + e), var = ei[e] & 0xfffffu;
                                 const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t + e)), (ei[e] >> 20) & 0xff, gf, a.offset, lane);
-                                store_record(ctov_f + (size_t)ed * rs, nr, n_m, lane);
+                                store_record(ctov_f, ed, rl, nr, n_m, lane);
                                 float mcv[VPL];
                                 expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr[e]), mcv);     /* :262-281 */
 #pragma unroll
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
-                                store_row<Q>(app_f + (size_t)var * Q, lane, v[e]);
+                                store_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v[e]);
                                 if (ei[e] >> 28) {                                                     /* tools.c:312 fused */
                                     const int d = warp_argmin<Q>(v[e], lane);
                                     if (lane == 0) dec_f[var] = (uint8_t)d;
@@ -649,7 +649,7 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     /* per-warp scratch area: scr[NE] | sel[NE] | mask | meta */
     int wa = NE * scr_words(k.q) * 4;
     k.wa_sel = wa; wa += NE * 36 * 4;
-    k.wa_mask = wa; wa += (k.q > 64) ? 8 * 32 * 4 : 0;
+    k.wa_mask = 0;                       /* the ES 'seen' mask (q = 256: 1 KiB) aliases scr[0]: phases never overlap in a warp */
     k.wa_meta = wa; wa += cpw * 16;
     k.wa_bytes = align_up(wa, 16);
     k.off_wa = off; off += nw * k.wa_bytes;
@@ -711,15 +711,16 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
 
     /* launch geometry: shared-memory budget -> warps per CTA, check nodes per warp, frames per group, step schedule */
     if (N >= (1 << 20) || E >= (1 << 24)) { ctx_err(c, "code too large for the packed graph tables (N < 2^20, E < 2^24)"); nbgpu_destroy(c); return NBGPU_EINVAL; }
-    const int budget = getenv("NBGPU_SMEM_KB") ? atoi(getenv("NBGPU_SMEM_KB")) * 1024 : 216 * 1024;
+    const int budget = getenv("NBGPU_SMEM_KB") ? atoi(getenv("NBGPU_SMEM_KB")) * 1024 : (CTAS_PER_SM > 1 ? (227 * 1024) / CTAS_PER_SM - 1024 : 216 * 1024);
     k.F = 1;
     int nw = getenv("NBGPU_WARPS") ? atoi(getenv("NBGPU_WARPS")) : NT_MAX / 32, cpw = getenv("NBGPU_CPW") ? atoi(getenv("NBGPU_CPW")) : 8;
+    /* the register budget is what limits residency: keep all NT_MAX/32 warps and shrink the tile before dropping warps */
     nw = std::max(1, std::min(nw, NT_MAX / 32)); cpw = std::max(1, std::min(cpw, 32));
     if (p->cns_per_step > 0) cpw = std::max(1, std::min(cpw, (p->cns_per_step + nw - 1) / nw));
     for (;;) {
         plan_smem(k, nw, cpw);
         if (k.smem_bytes <= budget) break;
-        if (nw > 8) nw -= 2; else if (cpw > 1) cpw--; else if (nw > 1) nw--; else break;
+        if (cpw > 4) cpw--; else if (nw > 8) nw -= 2; else if (cpw > 1) cpw--; else if (nw > 1) nw--; else break;
     }
     if (k.smem_bytes > 227 * 1024) { ctx_err(c, "decoder working set does not fit in shared memory (%d bytes for one warp)", k.smem_bytes); nbgpu_destroy(c); return NBGPU_EINVAL; }
     const int G = k.cap;

@@ -27,7 +27,7 @@
 template <int Q> struct QTraits {
     static constexpr int VPL = (Q >= 32) ? Q / 32 : 1;      /* values per lane when a warp holds one row */
     static constexpr int LOGQ = (Q == 16) ? 4 : (Q == 64) ? 6 : 8;
-    static constexpr int SCR_WORDS = (VPL + 1) * 32 > Q ? (VPL + 1) * 32 : Q;   /* per-edge scratch, u32 words */
+    static constexpr int SCR_WORDS = (VPL + 2) * 32 > Q ? (VPL + 2) * 32 : Q;   /* per-edge scratch, u32 words */
 };
 
 /* GF(q) helpers shared by every kernel: byte tables in shared memory (+ global fallback tables) */
@@ -89,10 +89,15 @@ template <int Q> __device__ __forceinline__ void store_row(float *row, int lane,
 }
 template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, float x)
 {
-    float v[QTraits<Q>::VPL];
-#pragma unroll
-    for (int j = 0; j < QTraits<Q>::VPL; j++) v[j] = x;
-    store_row<Q>(row, lane, v);
+    if constexpr (Q == 256) {
+        const float4 q4 = make_float4(x, x, x, x);
+        reinterpret_cast<float4 *>(row)[lane * 2] = q4;
+        reinterpret_cast<float4 *>(row)[lane * 2 + 1] = q4;
+    } else if constexpr (Q == 64) {
+        reinterpret_cast<float2 *>(row)[lane] = make_float2(x, x);
+    } else {
+        if (lane < Q) row[lane] = x;
+    }
 }
 
 /* ---- stored C->V message of one edge ("record"): llr[n_m] f32 | sat f32 | stp i32 | sym[n_m] u8 ----
@@ -101,16 +106,32 @@ template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, 
 struct RecView {
     float llr; int sym; float sat; int stp;     /* llr/sym: entry 'lane' (garbage for lane >= stp) */
 };
-__device__ __forceinline__ RecView load_record(const uint8_t *rec, int n_m, int lane)
+/* Per-lane byte offsets into a record, computed once per kernel: the record of edge 'ed' of a frame is
+ * at ctov_f + ed * stride, so a field address is one 32x32->64 multiply-add away. */
+struct RecLane {
+    uint32_t llr, sym, tail, stride;    /* byte offsets of llr[lane'], sym[lane'], {sat,stp}; lane' = lane < n_m ? lane : 0 */
+    __device__ __forceinline__ RecLane(int n_m, int lane, int rec_stride)
+    {
+        const int k = lane < n_m ? lane : 0;
+        llr = 4 * k; sym = 4 * n_m + 8 + k; tail = 4 * n_m; stride = (uint32_t)rec_stride;
+    }
+};
+__device__ __forceinline__ RecView load_record(const uint8_t *ctov_f, uint32_t ed, const RecLane &rl)
 {
     RecView r;
-    const int k = lane < n_m ? lane : 0;
-    r.llr = reinterpret_cast<const float *>(rec)[k];
-    const int2 tail = *reinterpret_cast<const int2 *>(rec + 4 * n_m);
+    const uint8_t *rec = ctov_f + (size_t)ed * rl.stride;
+    r.llr = *reinterpret_cast<const float *>(rec + rl.llr);
+    const int2 tail = *reinterpret_cast<const int2 *>(rec + rl.tail);
     r.sat = __int_as_float(tail.x);
     r.stp = tail.y;
-    r.sym = rec[4 * n_m + 8 + k];
+    r.sym = rec[rl.sym];
     return r;
+}
+__device__ __forceinline__ void store_record(uint8_t *ctov_f, uint32_t ed, const RecLane &rl, const RecView &r, int n_m, int lane)
+{
+    uint8_t *rec = ctov_f + (size_t)ed * rl.stride;
+    if (lane < n_m) { *reinterpret_cast<float *>(rec + rl.llr) = r.llr; rec[rl.sym] = (uint8_t)r.sym; }
+    if (lane == 0) *reinterpret_cast<int2 *>(rec + rl.tail) = make_int2(__float_as_int(r.sat), r.stp);
 }
 /* dense values of this lane's symbols; scr = per-edge scratch (>= q floats), free on return */
 template <int Q>
@@ -228,7 +249,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
     constexpr int LOGQ = QTraits<Q>::LOGQ;
     const bool active = (Q >= 32) || lane < Q;
     const int rounds = (n_m + 1 < Q) ? n_m + 1 : Q;
-    uint32_t head[NE], nxt[NE], selp[NE];
+    uint32_t head[NE], nkey[NE], nxt[NE], selp[NE];   /* head = smallest unpopped key of the lane, nkey = the one after it (register resident: no load on the REDUX chain) */
     bool bad[NE];
 #pragma unroll
     for (int e = 0; e < NE; e++) {
@@ -241,10 +262,12 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         sort_keys<VPL>(key);
         bad[e] = active && key[VPL - 1] >= 0x7f800000u;
 #pragma unroll
-        for (int j = 1; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
+        for (int j = 2; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
         scr[e][VPL * 32 + lane] = NB_KEY_INF;
+        scr[e][(VPL + 1) * 32 + lane] = NB_KEY_INF;
         head[e] = key[0];
-        nxt[e] = smem_u32(scr[e] + 32 + lane);
+        nkey[e] = VPL > 1 ? key[VPL > 1 ? 1 : 0] : NB_KEY_INF;
+        nxt[e] = smem_u32(scr[e] + (VPL > 1 ? 64 : 32) + lane);
         selp[e] = smem_u32(sel[e]);
     }
     /* no __syncwarp needed: every lane only reads back what it wrote itself */
@@ -254,11 +277,12 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                  ".reg .u32 m;\n\t"                                                                             \
                  "redux.sync.min.u32 m, %0, 0xffffffff;\n\t"                                                    \
                  "setp.eq.u32 p, %0, m;\n\t"                                                                    \
-                 "@p st.shared.u32 [%2+" #OFF "], %0;\n\t"                                                      \
-                 "@p ld.shared.u32 %0, [%1];\n\t"                                                               \
-                 "@p add.u32 %1, %1, 128;\n\t"                                                                  \
+                 "@p st.shared.u32 [%3+" #OFF "], %0;\n\t"                                                      \
+                 "@p mov.u32 %0, %1;\n\t"                                                                       \
+                 "@p ld.shared.u32 %1, [%2];\n\t"                                                               \
+                 "@p add.u32 %2, %2, 128;\n\t"                                                                  \
                  "}"                                                                                             \
-                 : "+r"(head[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
+                 : "+r"(head[E]), "+r"(nkey[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
     int r = 0;
     for (; r + 4 <= rounds; r += 4) {
 #pragma unroll
