@@ -14,6 +14,11 @@
  *                        (the true syndrome is still traced)
  *   NBREF_DIALECT=kn     parse the matrix with the reference's KN branch (init.c:211-227)
  *   NBREF_SUMMARY=<file> append one line "frames decode_s channel_s passes" at exit
+ *   NBREF_ECN=syndrome   the check node is the reference's syndrome_ems (syndrome_decoder.c:26) instead of
+ *                        CheckPassLogEMS -- i.e. NB_LDPC.c:388 un-commented and :392 commented -- with the
+ *                        table of NB_LDPC.c:189-201 built by the reference's own build_config_table +
+ *                        sort_config_table.  NBREF_SYND="d1,d2,d3,trunc,ncv" (default 19,15,5,1000,25; the
+ *                        values in the commented code, d_1=40, overrun the n_m-wide message rows)
  *
  * Trace record: int32 tag, int32 payload_bytes, payload.
  *   tag 1 HEADER  int32[8]  N M GF logGF nbMax nbBranch dc0 NbOper
@@ -33,6 +38,7 @@
 #include "tools.h"
 #include "channel.h"
 #include "bubble_decoder.h"
+#include "syndrome_decoder.h"
 
 void LoadCode_KN(char *FileMatrix, code_t *code);
 int ref_main(int argc, char *argv[]);
@@ -120,6 +126,27 @@ void probe_Channel(code_t *code, decoder_t *decoder, table_t *table, int **NBIN,
     clock_gettime(CLOCK_MONOTONIC, &g_t0);   /* decode time starts when the channel returns */
 }
 
+static int g_synd = -1, g_cfg_size, g_ncv;
+static int **g_cfg;
+static void check_node(int node, decoder_t *decoder, code_t *code, table_t *table, int NbOper, float offset)
+{
+    if (g_synd < 0) {
+        const char *e = getenv("NBREF_ECN");
+        g_synd = (e && strcmp(e, "syndrome") == 0);
+        if (g_synd) {
+            int d1 = 19, d2 = 15, d3 = 5, trunc = 1000, dc = code->rowDegree[0];
+            g_ncv = 25;
+            const char *p = getenv("NBREF_SYND");
+            if (p) sscanf(p, "%d,%d,%d,%d,%d", &d1, &d2, &d3, &trunc, &g_ncv);
+            g_cfg = build_config_table(&g_cfg_size, dc, d1, d2, d3);
+            sort_config_table(g_cfg, g_cfg_size, dc);
+            if (trunc > 0 && trunc < g_cfg_size) g_cfg_size = trunc;
+        }
+    }
+    if (g_synd) syndrome_ems(node, decoder, code, table, g_cfg, g_cfg_size, code->rowDegree[node], offset, g_ncv);
+    else CheckPassLogEMS(node, decoder, code, table, NbOper, offset);
+}
+
 void probe_CheckPass(int node, decoder_t *decoder, code_t *code, table_t *table, int NbOper, float offset)
 {
     g_NbOper = NbOper;
@@ -131,7 +158,7 @@ void probe_CheckPass(int node, decoder_t *decoder, code_t *code, table_t *table,
             il[t * nm + k] = decoder->M_VtoC_LLR[t][k];
             ig[t * nm + k] = (short)decoder->M_VtoC_GF[t][k];
         }
-        CheckPassLogEMS(node, decoder, code, table, NbOper, offset);
+        check_node(node, decoder, code, table, NbOper, offset);
         short *og = malloc(sizeof(short) * dc * GF);
         float *ol = malloc(sizeof(float) * dc * GF);
         for (t = 0; t < dc; t++) for (k = 0; k < GF; k++) {
@@ -146,7 +173,7 @@ void probe_CheckPass(int node, decoder_t *decoder, code_t *code, table_t *table,
         free(il); free(ig); free(ol); free(og);
         return;
     }
-    CheckPassLogEMS(node, decoder, code, table, NbOper, offset);
+    check_node(node, decoder, code, table, NbOper, offset);
 }
 
 static float **g_app;

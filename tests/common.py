@@ -45,6 +45,8 @@ class Golden:
         self.synd = z["synd"]
         self.app_sha = z["app_sha"]
         self.llr_sha = z["llr_sha"]
+        # (d1, d2, d3, trunc, n_cv) when the fixture was produced with the reference's syndrome_ems as check node
+        self.synd_params = tuple(int(x) for x in z["synd_params"]) if "synd_params" in z else None
 
     def final(self, f, nb_iter_max=None):
         """(decide, synd, iters) the reference reports for frame f when run with nb_iter_max (<= the fixture's)."""

@@ -40,6 +40,11 @@ CASES = [
     ("declercq_r12_gf64_nm20", 2, 10, "matrices/MatDeclercq_R12_GF64", 1.2, 20, 0.3, 25, 2, False, 0, "ubs"),
     ("ahmed_r34_gf16_nm16", 2, 10, "matrices/Ahmed_64800_R34_GF16", 3.0, 16, 0.3, 25, 2, False, 0, "ubs"),
     ("ad_r12_gf256_nm20", 2, 10, "matrices/AD_64800_R12_GF256", 2.0, 20, 0.3, 25, 2, False, 0, "ubs"),
+    # check node = the reference's syndrome_ems (NB_LDPC.c:388 instead of :392); last field = (d1, d2, d3, trunc, n_cv)
+    ("n96_gf64_nm20_synd", 12, 10, "matrices/N96_K48_GF64", 2.0, 20, 0.3, 25, 3, True, 1, "ubs", (19, 15, 5, 1000, 25)),
+    ("mat24_n480_nm20_synd", 4, 10, "matrices/Mat24_N480_M240", 1.5, 20, 0.3, 25, 2, False, 0, "ubs", (19, 15, 5, 1000, 25)),
+    ("mat24_n480_nm16_synd_small", 3, 10, "matrices/Mat24_N480_M240", 1.5, 16, 0.3, 25, 2, False, 0, "ubs", (15, 6, 3, 150, 12)),
+    ("ad_r12_gf256_nm20_synd", 1, 10, "matrices/AD_64800_R12_GF256", 2.0, 20, 0.3, 25, 2, False, 0, "ubs", (19, 15, 5, 1000, 25)),
 ]
 
 
@@ -48,10 +53,11 @@ def sha(a):
 
 
 def make(case):
-    name, frames, iters, matrix, ebn, n_m, offset, nbop, level, keep_llr, keep_cn, dialect = case
+    name, frames, iters, matrix, ebn, n_m, offset, nbop, level, keep_llr, keep_cn, dialect = case[:12]
+    synd = case[12] if len(case) > 12 else None
     with tempfile.TemporaryDirectory() as td:
         tr = os.path.join(td, "trace.bin")
-        out = ol.run_probe([frames, iters, matrix, ebn, n_m, offset, nbop], trace=tr, level=level, dialect=dialect)
+        out = ol.run_probe([frames, iters, matrix, ebn, n_m, offset, nbop], trace=tr, level=level, dialect=dialect, synd=synd)
         t = ol.read_trace(tr)
     h = t["header"]
     fr = t["frames"]
@@ -59,6 +65,8 @@ def make(case):
     N = h["N"]
     d = dict(args=np.array([frames, iters, n_m, nbop], np.int32), ebn=np.float32(ebn), offset=np.float32(offset),
              matrix=matrix, dialect=dialect, header=np.array([h["N"], h["M"], h["GF"], h["logGF"], h["E"]], np.int32))
+    if synd:
+        d["synd_params"] = np.array(synd, np.int32)
     nf = len(fr)
     d["nbin"] = np.stack([f["nbin"] for f in fr]).astype(np.int8)
     d["npasses"] = np.array([len(f["passes"]) for f in fr], np.int32)
@@ -86,16 +94,21 @@ def make(case):
     if keep_llr:
         d["llr"] = np.stack(llrs)
     if keep_cn:
-        cn_in_l, cn_in_g, cn_out_l, cn_node = [], [], [], []
+        cn_in_l, cn_in_g, cn_out_l, cn_node, cn_out_g = [], [], [], [], []
         for f in fr[:keep_cn]:
             for c in f["cn"]:
                 cn_node.append(c["node"]); cn_in_l.append(c["in_llr"]); cn_in_g.append(c["in_gf"])
                 cn_out_l.append(c["out_llr"])
-                assert (c["out_gf"] == np.arange(h["GF"])[None, :]).all()
+                if synd:
+                    cn_out_g.append(c["out_gf"])
+                else:
+                    assert (c["out_gf"] == np.arange(h["GF"])[None, :]).all()
         d["cn_node"] = np.array(cn_node, np.int32)
         d["cn_in_llr"] = np.stack(cn_in_l)
         d["cn_in_gf"] = np.stack(cn_in_g).astype(np.int16)
         d["cn_out_llr"] = np.stack(cn_out_l)
+        if synd:
+            d["cn_out_gf"] = np.stack(cn_out_g).astype(np.int16)
     m = re.findall(r"<\d+> FER=\s*(\d+)\s*/\s*(\d+)\s*=\s*[\d.]+\s*BER=\s*(\d+)\s*/\s*x\s*=\s*[\d.eE+-]+\s*avr_it=([\d.]+)", out)
     d["console"] = np.array([float(x) for x in m[-1]]) if m else np.zeros(4)
     path = os.path.join(HERE, name + ".npz")

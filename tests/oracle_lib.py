@@ -333,7 +333,7 @@ class RefShim:
         return cl, cg
 
 
-def run_probe(args, trace=None, level=1, force=False, dialect="ubs", summary=None, cwd=None):
+def run_probe(args, trace=None, level=1, force=False, dialect="ubs", summary=None, cwd=None, synd=None):
     """Run the interposed reference binary; args = [frames, iters, matrix, EbN, n_m, offset, nbOper]."""
     env = dict(os.environ)
     if trace:
@@ -343,6 +343,10 @@ def run_probe(args, trace=None, level=1, force=False, dialect="ubs", summary=Non
     env["NBREF_DIALECT"] = dialect
     if summary:
         env["NBREF_SUMMARY"] = summary
+    env.pop("NBREF_ECN", None)
+    if synd:                                   # (d1, d2, d3, trunc, n_cv): run the reference's syndrome_ems as check node
+        env["NBREF_ECN"] = "syndrome"
+        env["NBREF_SYND"] = ",".join(str(int(x)) for x in synd)
     cwd = cwd or REF_DIR
     os.makedirs(os.path.join(cwd, "data"), exist_ok=True)
     r = subprocess.run([os.path.join(REF_DIR, "essai_probe")] + [str(a) for a in args], cwd=cwd, env=env,

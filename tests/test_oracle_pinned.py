@@ -27,7 +27,11 @@ def test_oracle_reproduces_reference_run(name):
         assert sha(fr["llr"]) == g.llr_sha[f], "channel LLR differs"
         il, ig = o.sort_intrinsic(fr["llr"])
         assert sha(il) == g.z["illr_sha"][f] and sha(ig) == g.z["igf_sha"][f]
-        r = o.decode_frame(fr["llr"], g.n_m, g.nb_oper, g.nb_iter_max, g.offset, want_state=True)
+        kw = {}
+        if g.synd_params:                     # fixture produced with the reference's syndrome_ems as check node
+            d1, d2, d3, trunc, n_cv = g.synd_params
+            kw = dict(ecn=1, cfg=o.build_config_table(int(o.row_deg[0]), d1, d2, d3, trunc), n_cv=n_cv)
+        r = o.decode_frame(fr["llr"], g.n_m, g.nb_oper, g.nb_iter_max, g.offset, want_state=True, **kw)
         np_ = int(g.npasses[f])
         assert r["passes"] == np_
         assert (r["decide_trace"] == g.decide[f, :np_]).all()
@@ -44,7 +48,17 @@ def test_oracle_check_node_on_recorded_messages(name):
     g = Golden(name)
     o = ol.Oracle(matrix_path(g.matrix), g.dialect)
     z = g.z
+    cfg = None
+    if g.synd_params:
+        d1, d2, d3, trunc, n_cv = g.synd_params
+        cfg = o.build_config_table(int(o.row_deg[0]), d1, d2, d3, trunc)
     for i in range(len(z["cn_node"])):
+        if cfg is not None:
+            cl, cg = o.check_node_syndrome(int(z["cn_node"][i]), z["cn_in_llr"][i], z["cn_in_gf"][i].astype(np.int32), g.n_m, cfg,
+                                           g.offset, n_cv)
+            assert cl.tobytes() == z["cn_out_llr"][i].tobytes()
+            assert (cg == z["cn_out_gf"][i]).all()
+            continue
         cl, cg = o.check_node(int(z["cn_node"][i]), z["cn_in_llr"][i], z["cn_in_gf"][i].astype(np.int32), g.n_m, g.nb_oper,
                               g.offset)
         assert cl.tobytes() == z["cn_out_llr"][i].tobytes()
@@ -142,6 +156,41 @@ def test_check_node_equals_reference(rel, n_m, nb_oper, offset):
         x = r.check_node(node, vl, vg, nb_oper, offset)
         y = o.check_node(node, vl, vg, n_m, nb_oper, offset)
         assert x[0].tobytes() == y[0].tobytes() and (x[1] == y[1]).all(), k
+    o.close()
+
+
+def _synd_lists(rng, dc, n_m, GF, mode):
+    """V->C lists as the decode loop produces them: ascending from 0, distinct symbols; mode 1 adds exact ties."""
+    vl = np.sort(rng.random((dc, n_m)).astype(np.float32) * np.float32(rng.choice([1, 5, 20])), axis=1)
+    if mode == 1:
+        vl = (np.round(vl * 4) / 4).astype(np.float32)
+    vl[:, 0] = 0
+    vl = np.sort(vl, axis=1).astype(np.float32)
+    vg = np.stack([rng.permutation(GF)[:n_m] for _ in range(dc)]).astype(np.int32)
+    return vl, vg
+
+
+@needs_ref
+@pytest.mark.parametrize("rel,n_m,dd,trunc,n_cv", [("matrices/Mat24_N480_M240", 16, (15, 10, 5), 0, 20),
+                                                   ("matrices/AD_64800_R12_GF256", 20, (19, 15, 5), 1000, 25),
+                                                   ("matrices/N96_K48_GF64", 20, (19, 15, 5), 300, 25),
+                                                   ("matrices/Mat24_N48_M24", 8, (7, 4, 2), 0, 6)])
+def test_syndrome_check_node_equals_reference(rel, n_m, dd, trunc, n_cv):
+    """build_config_table + sort_config_table + syndrome_ems (presorting_mvc, sorting, bayes) vs the compiled reference."""
+    path = matrix_path(rel)
+    o = ol.Oracle(path, 1)
+    r = ol.RefShim(path, False, n_m)
+    dc = int(o.row_deg[0])
+    cfg = o.build_config_table(dc, *dd, trunc)
+    ref_cfg = r.build_config(dc, *dd, trunc)
+    assert cfg.shape == ref_cfg.shape and (cfg == ref_cfg).all()
+    rng = np.random.default_rng(11)
+    for it in range(120):
+        node = int(rng.integers(0, o.M))
+        vl, vg = _synd_lists(rng, dc, n_m, o.GF, it % 3)
+        cl, cg = o.check_node_syndrome(node, vl, vg, n_m, cfg, 0.3, n_cv)
+        rl, rg = r.syndrome_ems(node, vl, vg, dc, 0.3, n_cv)
+        assert cl.tobytes() == rl.tobytes() and (cg == rg).all()
     o.close()
 
 
