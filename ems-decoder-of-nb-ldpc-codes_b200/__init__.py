@@ -104,6 +104,7 @@ def lib():
         "nbgpu_select_nm": (C.c_int, [vp, _fp, _fp, _ip, C.c_int]),
         "nbgpu_decision_syndrome": (C.c_int, [vp, _fp, _ip, _ip, C.c_int]),
         "nbgpu_accumulate_stats": (C.c_int, [vp, _ip, _ip, _ip, _ip, C.c_int, _lp]),
+        "nbgpu_config_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
         "nbgpu_version": (C.c_char_p, []),
         "nbgpu_device_count": (C.c_int, []),
     }
@@ -365,6 +366,16 @@ class Decoder:
             self.close()
         except Exception:
             pass
+
+
+def config_table(dc, d1, d2, d3, trunc=0):
+    """nbgpu_config_table: the [size, dc] configuration table of the syndrome-based check node."""
+    size = lib().nbgpu_config_table(dc, d1, d2, d3, trunc, None, 0)
+    if size < 0:
+        _check(size)
+    t = np.zeros((size, dc), np.int32)
+    _check(min(lib().nbgpu_config_table(dc, d1, d2, d3, trunc, _i(t), size), 0))
+    return t
 
 
 def pin(arr):

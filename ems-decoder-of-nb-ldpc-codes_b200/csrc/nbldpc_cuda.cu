@@ -23,6 +23,7 @@
  * Every APP row is read twice (L2 hit the second time) and written once per edge visit.
  */
 #include "nbldpc_device.cuh"
+#include "nbldpc_synd.cuh"
 #include "nbldpc_internal.h"
 #include <cstdarg>
 #include <cstdio>
@@ -64,6 +65,11 @@ struct KArgs {
     int wa_sel, wa_mask, wa_meta;       /* offsets inside a warp's scratch area (scr at 0) */
     int lstride;                        /* bytes per list: n_m f32 | n_m u8 | len u8 | pad */
     int smem_bytes;
+    /* syndrome-based check node (ecn = 1): dense CtoV rows, configuration table, per-warp sort buffers */
+    int ecn, S, Spad, n_cv;
+    const uint8_t *cfg;                 /* [S][dc_max] u8 */
+    float *ctov_dense;                  /* [slots][E][q] f32 */
+    int off_cfg, sw_lists, sw_key, sw_pay, sw_gf, sw_hist, sw_M, sw_upd, sw_perm;   /* sw_*: offsets inside a warp's list area */
 };
 
 /* Lists of a warp's tile in shared memory, by 32-bit shared-window address.  c = check node of the
@@ -198,6 +204,36 @@ __device__ __forceinline__ void load_gf_tables(unsigned char *smem, const KArgs 
     gf.img = tab; gf.inv = tab + 256; gf.rotin = a.rotin; gf.rotout = a.rotout;
 }
 
+__device__ __forceinline__ SyndMem make_synd_mem(unsigned char *smem, const KArgs &a, int warp)
+{
+    SyndMem sm;
+    const uint32_t wb = smem_u32(smem + a.off_wb + warp * a.wb_bytes);
+    sm.lists = wb + a.sw_lists;
+    sm.key[0] = wb + a.sw_key; sm.key[1] = sm.key[0] + 4 * a.Spad;
+    sm.pay[0] = wb + a.sw_pay; sm.pay[1] = sm.pay[0] + 2 * a.Spad;
+    sm.gf = wb + a.sw_gf; sm.hist = wb + a.sw_hist; sm.M = wb + a.sw_M; sm.upd = wb + a.sw_upd; sm.perm = wb + a.sw_perm;
+    sm.cfg = smem_u32(smem + a.off_cfg);
+    sm.lstride = a.lstride; sm.n_m = a.n_m; sm.dc = a.dc_max; sm.S = a.S; sm.Spad = a.Spad; sm.n_cv = a.n_cv;
+    return sm;
+}
+__device__ __forceinline__ void load_cfg_table(unsigned char *smem, const KArgs &a)
+{
+    if (a.ecn != 1) return;
+    uint8_t *dst = smem + a.off_cfg;
+    for (int i = threadIdx.x; i < a.S * a.dc_max; i += blockDim.x) dst[i] = a.cfg[i];
+}
+/* dense output row of one edge from the syndrome check node: Mcv[s] = M[img(MULGF[s][h])] (syndrome_decoder.c:260-266
+ * followed by the scatter NB_LDPC.c:415-421) */
+template <int Q, bool CLOSED>
+__device__ __forceinline__ void synd_dense_row(const SyndMem &sm, const GFTab &gf, int h, int lane, float (&mcv)[QTraits<Q>::VPL])
+{
+#pragma unroll
+    for (int j = 0; j < QTraits<Q>::VPL; j++) {
+        const int s = lane * QTraits<Q>::VPL + j;
+        mcv[j] = (Q >= 32 || lane < Q) ? lds_f32(sm.M + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)) : NB_SENT;
+    }
+}
+
 /* L2 prefetch of the APP rows and CtoV records of up to NE consecutive edges (one instruction) */
 template <int Q>
 __device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t *ctov_f, const uint32_t *einfo, int ed, int n,
@@ -215,7 +251,7 @@ __device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t
     if (p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
-template <int Q, bool CLOSED>
+template <int Q, bool CLOSED, int ECN>
 __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs a)
 {
     constexpr int VPL = QTraits<Q>::VPL;
@@ -225,6 +261,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
     const Lists &ls = wm.ls;
     GFTab gf;
     load_gf_tables(smem, a, gf);
+    load_cfg_table(smem, a);
     int *misc = reinterpret_cast<int *>(smem + a.off_misc);
     int *s_base = misc;                 /* [1]  first frame of the group  */
     int *s_alive = misc + 1;            /* [1]  frames of the group still iterating */
@@ -237,6 +274,8 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
     float *app = a.app + blockIdx.x * F * frame_app;
     uint8_t *ctov = a.ctov + blockIdx.x * F * frame_ctov;
     uint8_t *dec = a.dec + (size_t)blockIdx.x * F * N;
+    const size_t frame_dense = (size_t)a.E * Q;
+    float *ctov_d = ECN == 1 ? a.ctov_dense + blockIdx.x * F * frame_dense : nullptr;
 
     for (;;) {
         __syncthreads();
@@ -254,8 +293,13 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
             else load_row<Q>(a.in + ((size_t)(base + f) * N + n) * Q, lane, v);
             store_row<Q>(app + ((size_t)f * N + n) * Q, lane, v);
         }
-        for (int i = tid; i < nf * a.E; i += nthr)           /* CtoV = 0: stp 0, constant 0.0f */
-            *reinterpret_cast<int2 *>(ctov + (size_t)i * rs + 4 * n_m) = make_int2(0, 0);
+        if constexpr (ECN == 0) {
+            for (int i = tid; i < nf * a.E; i += nthr)       /* CtoV = 0: stp 0, constant 0.0f */
+                *reinterpret_cast<int2 *>(ctov + (size_t)i * rs + 4 * n_m) = make_int2(0, 0);
+        } else {
+            float4 *z = reinterpret_cast<float4 *>(ctov_d);  /* CtoV = 0, NB_LDPC.c:273-279 */
+            for (size_t i = tid; i < (size_t)nf * frame_dense / 4; i += nthr) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int i = tid; i < F; i += nthr) { s_done[i] = (i < nf) ? 0 : -1; s_synd[i] = 0; }
         if (tid == 0) { *s_alive = nf; for (int f = 0; f < nf; f++) { a.frame_slot[base + f] = blockIdx.x * F + f; a.slot_frame[blockIdx.x * F + f] = base + f; } }
         __syncthreads();
@@ -282,6 +326,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                     wm.meta[lane] = make_int4(info & 0xffffff, s_done[f] ? 0 : (int)(info >> 24), f, 0);
                 }
                 __syncwarp();
+                if constexpr (ECN == 0) {
                 /* ---------------- phase 1 ---------------- */
                 for (int c = 0; c < cnt; c++) {
                     const int4 mt = wm.meta[c];
@@ -374,6 +419,66 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                                     if (lane == 0) dec_f[var] = (uint8_t)d;
                                 }
                             }
+                        }
+                    }
+                }
+                } else {
+                    /* ---------------- syndrome-based check node: one node at a time per warp ---------------- */
+                    const SyndMem sm = make_synd_mem(smem, a, warp);
+                    for (int c = 0; c < cnt; c++) {
+                        const int4 mt = wm.meta[c];
+                        const int e0 = mt.x, dc = mt.y;
+                        if (dc == 0) continue;
+                        float *app_f = app + mt.z * frame_app;
+                        float *cd_f = ctov_d + mt.z * frame_dense;
+                        uint8_t *dec_f = dec + mt.z * N;
+                        /* V->C messages of the node: Mvc = APP - CtoV, truncation, rotation (NB_LDPC.c:329-374, syndrome_decoder.c:41-48) */
+                        for (int t = 0; t < dc; t += NE) {
+                            float v[NE][VPL];
+                            int hv[NE];
+#pragma unroll
+                            for (int e = 0; e < NE; e++) {
+                                const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));
+                                const uint32_t ei = a.einfo[ed];
+                                hv[e] = (ei >> 20) & 0xff;
+                                float cv[VPL];
+                                load_row<Q>(app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q), lane, v[e]);
+                                load_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, cv);
+#pragma unroll
+                                for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);
+                            }
+                            float llr[NE]; int sym[NE];
+                            select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
+#pragma unroll
+                            for (int e = 0; e < NE; e++) {
+                                if (t + e < dc && lane < n_m) {
+                                    const uint32_t list = sm.lists + (t + e) * sm.lstride;
+                                    sts_f32(list + 4 * lane, llr[e]);
+                                    sts_u8(list + 4 * n_m + lane, (uint32_t)gf_rot_in<Q, CLOSED>(gf, sym[e], hv[e]));
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        synd_prepare(sm, lane);
+                        for (int d = 0; d < dc; d++) {
+                            synd_edge(sm, d, a.offset, lane);
+                            const int t = (int)lds_u32(sm.perm + 4 * d);                   /* un-permute, syndrome_decoder.c:234-253 */
+                            const uint32_t ed = (uint32_t)(e0 + t);
+                            const uint32_t ei = a.einfo[ed];
+                            const uint32_t var = ei & 0xfffffu;
+                            float mcv[VPL], v[VPL], cv[VPL];
+                            synd_dense_row<Q, CLOSED>(sm, gf, (ei >> 20) & 0xff, lane, mcv);
+                            load_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v);
+                            load_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, cv);
+#pragma unroll
+                            for (int j = 0; j < VPL; j++) v[j] = __fadd_rn(mcv[j], __fsub_rn(v[j], cv[j]));   /* NB_LDPC.c:334, 448 */
+                            store_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, mcv);                   /* NB_LDPC.c:438 */
+                            store_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v);
+                            if (ei >> 28) {
+                                const int dd = warp_argmin<Q>(v, lane);
+                                if (lane == 0) dec_f[var] = (uint8_t)dd;
+                            }
+                            __syncwarp();
                         }
                     }
                 }
@@ -498,6 +603,44 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
     }
 }
 
+/* one check node (syndrome ECN) for B input sets, one warp per set: cllr[t][k] = M_CtoV_LLR[t][k] with k the rotated
+ * symbol, cgf[t][k] = DIVGF[k][h_t] (syndrome_decoder.c:234-266) */
+template <int Q, bool CLOSED>
+__global__ void __launch_bounds__(NT_MAX, 1) checknode_synd_kernel(const KArgs a, int node, const float *vllr, const int *vgf,
+                                                                   float *cllr, int *cgf, int B)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    GFTab gf;
+    load_gf_tables(smem, a, gf);
+    load_cfg_table(smem, a);
+    __syncthreads();
+    const SyndMem sm = make_synd_mem(smem, a, warp);
+    const int e0 = a.row_ptr[node], dc = a.row_ptr[node + 1] - e0, n_m = a.n_m;
+    for (int b = blockIdx.x * nw + warp; b < B; b += gridDim.x * nw) {
+        for (int i = lane; i < dc * n_m; i += 32) {
+            const int t = i / n_m, k = i - t * n_m;
+            const size_t src = ((size_t)b * dc + t) * n_m + k;
+            const uint32_t list = sm.lists + t * sm.lstride;
+            sts_f32(list + 4 * k, vllr[src]);
+            sts_u8(list + 4 * n_m + k, (uint32_t)gf_rot_in<Q, CLOSED>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]));
+        }
+        __syncwarp();
+        synd_prepare(sm, lane);
+        for (int d = 0; d < dc; d++) {
+            synd_edge(sm, d, a.offset, lane);
+            const int t = (int)lds_u32(sm.perm + 4 * d);
+            float *dst = cllr + ((size_t)b * dc + t) * Q;
+            int *gdst = cgf + ((size_t)b * dc + t) * Q;
+            for (int k = lane; k < Q; k += 32) {
+                dst[k] = lds_f32(sm.M + 4 * gf.img[k]);
+                gdst[k] = gf_rot_out<Q, CLOSED>(gf, gf.img[k], a.hval[e0 + t]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 /* Decision + Syndrom on dense APP[B][N][q] */
 template <int Q>
 __global__ void __launch_bounds__(UNIT_NT) decision_kernel(const KArgs a, const float *app, int *decide, int B)
@@ -567,13 +710,18 @@ __global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const f
     }
 }
 
-static const void *decode_fn(int q, int closed)
+template <int ECN> static const void *decode_fn_e(int q, int closed)
 {
-    if (closed) return q == 16 ? (const void *)decode_kernel<16, true> : q == 64 ? (const void *)decode_kernel<64, true> : (const void *)decode_kernel<256, true>;
-    return q == 16 ? (const void *)decode_kernel<16, false> : q == 64 ? (const void *)decode_kernel<64, false> : (const void *)decode_kernel<256, false>;
+    if (closed) return q == 16 ? (const void *)decode_kernel<16, true, ECN> : q == 64 ? (const void *)decode_kernel<64, true, ECN> : (const void *)decode_kernel<256, true, ECN>;
+    return q == 16 ? (const void *)decode_kernel<16, false, ECN> : q == 64 ? (const void *)decode_kernel<64, false, ECN> : (const void *)decode_kernel<256, false, ECN>;
 }
-static const void *checknode_fn(int q, int closed)
+static const void *decode_fn(int q, int closed, int ecn) { return ecn ? decode_fn_e<1>(q, closed) : decode_fn_e<0>(q, closed); }
+static const void *checknode_fn(int q, int closed, int ecn)
 {
+    if (ecn) {
+        if (closed) return q == 16 ? (const void *)checknode_synd_kernel<16, true> : q == 64 ? (const void *)checknode_synd_kernel<64, true> : (const void *)checknode_synd_kernel<256, true>;
+        return q == 16 ? (const void *)checknode_synd_kernel<16, false> : q == 64 ? (const void *)checknode_synd_kernel<64, false> : (const void *)checknode_synd_kernel<256, false>;
+    }
     if (closed) return q == 16 ? (const void *)checknode_kernel<16, true> : q == 64 ? (const void *)checknode_kernel<64, true> : (const void *)checknode_kernel<256, true>;
     return q == 16 ? (const void *)checknode_kernel<16, false> : q == 64 ? (const void *)checknode_kernel<64, false> : (const void *)checknode_kernel<256, false>;
 }
@@ -595,6 +743,7 @@ struct nbgpu_ctx {
     /* device buffers */
     int *d_row_ptr, *d_col, *d_step_ptr, *d_isolated;
     uint32_t *d_cninfo, *d_einfo;
+    uint8_t *d_cfg; float *d_ctov_dense;
     uint8_t *d_hval, *d_rotin, *d_rotout, *d_img, *d_inv;
     float *d_app; uint8_t *d_ctov; uint8_t *d_dec;
     float *d_in; size_t in_capacity;
@@ -656,6 +805,20 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     /* per-warp lists: cpw nodes x L lists x {n_m f32 | n_m u8 | len u8} */
     k.lstride = align_up(5 * k.n_m + 1, 4);
     k.wb_bytes = align_up(cpw * k.L * k.lstride, 16);
+    if (k.ecn == 1) {
+        /* syndrome check node: CTA-wide configuration table, then per warp: lists | keys x2 | payload x2 | gf | hist | M | upd | perm */
+        k.off_cfg = off; off += align_up(k.S * k.dc_max, 16);
+        int wb2 = 0;
+        k.sw_lists = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
+        k.sw_key = wb2; wb2 += 2 * 4 * k.Spad;
+        k.sw_pay = wb2; wb2 += 2 * 2 * k.Spad;
+        k.sw_gf = wb2; wb2 += k.Spad;
+        k.sw_hist = wb2; wb2 += 256 * 4;
+        k.sw_M = wb2; wb2 += 256 * 4;
+        k.sw_upd = wb2; wb2 += 256;
+        k.sw_perm = wb2; wb2 += 80;
+        k.wb_bytes = align_up(wb2, 16);
+    }
     k.off_wb = off; off += nw * k.wb_bytes;
     k.smem_bytes = off + 256;            /* slack: select_edges may read one key row past a sentinel row */
 }
@@ -664,7 +827,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
 {
     *out = NULL;
     if (!code || !p) { ctx_err(NULL, "nbgpu_create: NULL argument"); return NBGPU_EINVAL; }
-    if (p->ecn_kind != 0) { ctx_err(NULL, "ecn_kind %d: only the L-Bubble check node (0) is built in this version", p->ecn_kind); return NBGPU_EINVAL; }
+    if (p->ecn_kind != 0 && p->ecn_kind != 1) { ctx_err(NULL, "ecn_kind %d unknown (0 = CheckPassLogEMS, 1 = syndrome_ems)", p->ecn_kind); return NBGPU_EINVAL; }
     if (p->n_m < 5 || p->n_m > 32 || p->n_m > code->q) { ctx_err(NULL, "n_m=%d unsupported: need 5 <= n_m <= min(q,32) (ElementaryStep reads row 4, bubble_decoder.c:457)", p->n_m); return NBGPU_EINVAL; }
     if (p->nb_iter_max < 2) { ctx_err(NULL, "nb_iter_max must be >= 2 (nb_iter_max-1 passes are run, NB_LDPC.c:314)"); return NBGPU_EINVAL; }
     if (p->nb_oper < 1) { ctx_err(NULL, "nb_oper must be >= 1"); return NBGPU_EINVAL; }
@@ -709,18 +872,45 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     c->row_ptr_h = (int *)malloc(sizeof(int) * (M + 1)); memcpy(c->row_ptr_h, code->row_ptr, sizeof(int) * (M + 1));
     c->inv_h = (int *)malloc(sizeof(int) * q); memcpy(c->inv_h, code->inv, sizeof(int) * q);
 
+    /* syndrome-based check node: parameters of NB_LDPC.c:185-201 (commented out there), validated so that every index the
+     * reference would use stays inside its arrays (d_1 = 40 of the commented code overruns the n_m-wide rows) */
+    std::vector<uint8_t> cfg8;
+    k.ecn = p->ecn_kind;
+    if (p->ecn_kind == 1) {
+        const int dc = code->dc_max, nm1 = p->n_m - 1;
+        const int d1 = p->d1 > 0 ? p->d1 : nm1, d2 = p->d2 > 0 ? p->d2 : std::min(15, nm1), d3 = p->d3 > 0 ? p->d3 : std::min(5, nm1);
+        const int trunc = p->cfg_trunc > 0 ? p->cfg_trunc : 1000, n_cv = p->n_cv > 0 ? p->n_cv : p->nb_oper;
+        if (p->border != 0 && p->border != 4) { ctx_err(c, "border=%d: syndrome_ems fixes border = 4 (syndrome_decoder.c:56)", p->border); nbgpu_destroy(c); return NBGPU_EINVAL; }
+        if (code->dc_min != dc || dc < 4 || dc > 8) { ctx_err(c, "syndrome_ems needs a check-regular code with 4 <= dc <= 8 (dc = %d..%d)", code->dc_min, dc); nbgpu_destroy(c); return NBGPU_EINVAL; }
+        if (d1 > nm1 || d2 > nm1 || d3 > nm1 || p->n_m < 3) { ctx_err(c, "deviations (%d,%d,%d) exceed the list length n_m-1 = %d", d1, d2, d3, nm1); nbgpu_destroy(c); return NBGPU_EINVAL; }
+        int size = 0;
+        int *tab = nbgpu_build_config_table(dc, d1, d2, d3, trunc, &size);
+        if (!tab || size < 1) { ctx_err(c, "cannot build the configuration table"); nbgpu_destroy(c); return NBGPU_ENOMEM; }
+        if (size > NB_SYND_MAX) { free(tab); ctx_err(c, "%d configurations: at most %d are supported (use cfg_trunc)", size, NB_SYND_MAX); nbgpu_destroy(c); return NBGPU_EINVAL; }
+        cfg8.resize((size_t)size * dc);
+        for (int d = 0; d < dc; d++) {
+            int kept = 0;
+            for (int i = 0; i < size; i++) { cfg8[(size_t)i * dc + d] = (uint8_t)tab[(size_t)i * dc + d]; kept += tab[(size_t)i * dc + d] == 0; }
+            if (n_cv - 1 + 3 * d >= kept) { free(tab); ctx_err(c, "n_cv=%d: edge %d has only %d decorrelated syndromes, index %d is read (syndrome_decoder.c:195)", n_cv, d, kept, n_cv - 1 + 3 * d); nbgpu_destroy(c); return NBGPU_EINVAL; }
+        }
+        free(tab);
+        k.S = size; k.Spad = align_up(size, 32); k.n_cv = n_cv;
+    }
+
     /* launch geometry: shared-memory budget -> warps per CTA, check nodes per warp, frames per group, step schedule */
     if (N >= (1 << 20) || E >= (1 << 24)) { ctx_err(c, "code too large for the packed graph tables (N < 2^20, E < 2^24)"); nbgpu_destroy(c); return NBGPU_EINVAL; }
     const int budget = getenv("NBGPU_SMEM_KB") ? atoi(getenv("NBGPU_SMEM_KB")) * 1024 : (CTAS_PER_SM > 1 ? (227 * 1024) / CTAS_PER_SM - 1024 : 216 * 1024);
     k.F = 1;
     int nw = getenv("NBGPU_WARPS") ? atoi(getenv("NBGPU_WARPS")) : NT_MAX / 32, cpw = getenv("NBGPU_CPW") ? atoi(getenv("NBGPU_CPW")) : 8;
     /* the register budget is what limits residency: keep all NT_MAX/32 warps and shrink the tile before dropping warps */
+    if (p->ecn_kind == 1 && !getenv("NBGPU_CPW")) cpw = 4;       /* nodes of a tile are processed one after the other: no shared-memory cost */
     nw = std::max(1, std::min(nw, NT_MAX / 32)); cpw = std::max(1, std::min(cpw, 32));
     if (p->cns_per_step > 0) cpw = std::max(1, std::min(cpw, (p->cns_per_step + nw - 1) / nw));
     for (;;) {
         plan_smem(k, nw, cpw);
         if (k.smem_bytes <= budget) break;
-        if (cpw > 4) cpw--; else if (nw > 8) nw -= 2; else if (cpw > 1) cpw--; else if (nw > 1) nw--; else break;
+        if (p->ecn_kind == 1) { if (nw > 1) nw--; else break; }
+        else if (cpw > 4) cpw--; else if (nw > 8) nw -= 2; else if (cpw > 1) cpw--; else if (nw > 1) nw--; else break;
     }
     if (k.smem_bytes > 227 * 1024) { ctx_err(c, "decoder working set does not fit in shared memory (%d bytes for one warp)", k.smem_bytes); nbgpu_destroy(c); return NBGPU_EINVAL; }
     const int G = k.cap;
@@ -765,13 +955,14 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
         (rc = upload(c, &c->d_step_ptr, step_ptr)) || (rc = upload(c, &c->d_isolated, isolated)) || (rc = upload(c, &c->d_hval, hval)) ||
         (rc = upload(c, &c->d_rotin, rotin)) || (rc = upload(c, &c->d_rotout, rotout)) ||
         (rc = upload(c, &c->d_img, img)) || (rc = upload(c, &c->d_inv, inv))) { nbgpu_destroy(c); return rc; }
+    if (p->ecn_kind == 1) { if ((rc = upload(c, &c->d_cfg, cfg8))) { nbgpu_destroy(c); return rc; } k.cfg = c->d_cfg; }
     k.row_ptr = c->d_row_ptr; k.col = c->d_col; k.cninfo = c->d_cninfo; k.einfo = c->d_einfo; k.step_ptr = c->d_step_ptr; k.isolated = c->d_isolated;
     k.hval = c->d_hval; k.rotin = c->d_rotin; k.rotout = c->d_rotout; k.img = c->d_img; k.inv = c->d_inv;
 
     /* persistent grid: one CTA per SM */
-    const void *fn = decode_fn(q, k.gf_closed);
+    const void *fn = decode_fn(q, k.gf_closed, k.ecn);
     CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
-    const void *fn2 = checknode_fn(q, k.gf_closed);
+    const void *fn2 = checknode_fn(q, k.gf_closed, k.ecn);
     CK(c, cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
     int per_sm = 0;
     CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, k.nw * 32, k.smem_bytes, cudaOccupancyDefault));
@@ -784,7 +975,8 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     c->nslots = c->grid * k.F;
 
     CK(c, cudaMalloc((void **)&c->d_app, (size_t)c->nslots * N * q * sizeof(float)));
-    CK(c, cudaMalloc((void **)&c->d_ctov, (size_t)c->nslots * E * k.rec_stride + 512));
+    CK(c, cudaMalloc((void **)&c->d_ctov, (p->ecn_kind == 1 ? 0 : (size_t)c->nslots * E * k.rec_stride) + 512));
+    if (p->ecn_kind == 1) CK(c, cudaMalloc((void **)&c->d_ctov_dense, (size_t)c->nslots * E * q * sizeof(float)));
     CK(c, cudaMalloc((void **)&c->d_dec, (size_t)c->nslots * N));
     CK(c, cudaMemset(c->d_dec, 0, (size_t)c->nslots * N));
     CK(c, cudaMalloc((void **)&c->d_decide, (size_t)max_batch * N * sizeof(int)));
@@ -796,7 +988,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     CK(c, cudaMalloc((void **)&c->d_queue, 2 * sizeof(unsigned)));
     c->d_slow = c->d_queue + 1;
     CK(c, cudaMemset(c->d_queue, 0, 2 * sizeof(unsigned)));
-    k.app = c->d_app; k.ctov = c->d_ctov; k.dec = c->d_dec;
+    k.app = c->d_app; k.ctov = c->d_ctov; k.dec = c->d_dec; k.ctov_dense = c->d_ctov_dense;
     k.out_decide = c->d_decide; k.out_synd = c->d_synd; k.out_iters = c->d_iters;
     k.frame_slot = c->d_frame_slot; k.slot_frame = c->d_slot_frame; k.queue = c->d_queue; k.slow_counter = c->d_slow;
     *out = c;
@@ -807,7 +999,7 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    void *bufs[] = { c->d_row_ptr, c->d_col, c->d_cninfo, c->d_einfo, c->d_step_ptr, c->d_isolated, c->d_hval, c->d_rotin,
+    void *bufs[] = { c->d_cfg, c->d_ctov_dense, c->d_row_ptr, c->d_col, c->d_cninfo, c->d_einfo, c->d_step_ptr, c->d_isolated, c->d_hval, c->d_rotin,
                      c->d_rotout, c->d_img, c->d_inv, c->d_app, c->d_ctov, c->d_dec, c->d_in, c->d_decide, c->d_synd,
                      c->d_iters, c->d_frame_slot, c->d_slot_frame, c->d_queue };
     for (void *b : bufs) if (b) cudaFree(b);
@@ -866,7 +1058,7 @@ extern "C" int nbgpu_run(nbgpu_ctx *c)
     CK(c, cudaEventRecord(c->ev0, c->stream));
     {
         void *args[] = { (void *)&k };
-        CK(c, cudaLaunchKernel(decode_fn(c->q, k.gf_closed), dim3(grid), dim3(k.nw * 32), args, k.smem_bytes, c->stream));
+        CK(c, cudaLaunchKernel(decode_fn(c->q, k.gf_closed, k.ecn), dim3(grid), dim3(k.nw * 32), args, k.smem_bytes, c->stream));
     }
     CK(c, cudaGetLastError());
     CK(c, cudaEventRecord(c->ev1, c->stream));
@@ -972,7 +1164,9 @@ extern "C" int nbgpu_get_state(nbgpu_ctx *c, int frame, float *APP, float *CtoV)
     if (owner != frame) { ctx_err(c, "state of frame %d was overwritten by frame %d (batch larger than the resident slots)", frame, owner); return NBGPU_ESTATE; }
     const int N = c->N, q = c->q, E = c->E, n_m = c->p.n_m, rs = c->k.rec_stride;
     if (APP) CK(c, cudaMemcpy(APP, c->d_app + (size_t)slot * N * q, (size_t)N * q * sizeof(float), cudaMemcpyDeviceToHost));
-    if (CtoV) {
+    if (CtoV && c->k.ecn == 1) {
+        CK(c, cudaMemcpy(CtoV, c->d_ctov_dense + (size_t)slot * E * q, (size_t)E * q * sizeof(float), cudaMemcpyDeviceToHost));
+    } else if (CtoV) {
         std::vector<uint8_t> rec((size_t)E * rs);
         CK(c, cudaMemcpy(rec.data(), c->d_ctov + (size_t)slot * E * rs, rec.size(), cudaMemcpyDeviceToHost));
         for (int e = 0; e < E; e++) {
@@ -1072,11 +1266,11 @@ extern "C" int nbgpu_check_node(nbgpu_ctx *c, int node, const float *vllr, const
     CK(c, dcl.alloc((size_t)B * dc * q)); CK(c, dcg.alloc((size_t)B * dc * q));
     CK(c, cudaMemcpy(dvl.p, vllr, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(dvg.p, vgf, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
-    const int grid = std::min((B + c->k.cap - 1) / c->k.cap, 148);
+    const int grid = c->k.ecn == 1 ? std::min((B + c->k.nw - 1) / c->k.nw, 148) : std::min((B + c->k.cap - 1) / c->k.cap, 148);
     {
         const float *a1 = dvl.p; const int *a2 = dvg.p; float *a3 = dcl.p; int *a4 = dcg.p;
         void *args[] = { (void *)&c->k, (void *)&node, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&B };
-        CK(c, cudaLaunchKernel(checknode_fn(q, c->k.gf_closed), dim3(grid), dim3(c->k.nw * 32), args, c->k.smem_bytes, c->stream));
+        CK(c, cudaLaunchKernel(checknode_fn(q, c->k.gf_closed, c->k.ecn), dim3(grid), dim3(c->k.nw * 32), args, c->k.smem_bytes, c->stream));
     }
     CK(c, cudaGetLastError());
     c->launches++;

@@ -433,3 +433,72 @@ void nbgpu_free_schedule(nbgpu_schedule *s)
     free(s->step_ptr); free(s->order);
     s->step_ptr = NULL; s->order = NULL; s->nsteps = 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Configuration table of the syndrome-based check node: what build_config_table
+ * (syndrome_decoder.c:1542; generator gen_config_table2, :1661-1767) followed by sort_config_table
+ * (:2285-2371) and the truncation of NB_LDPC.c:198-201 produce.  A configuration gives, per edge of
+ * the check node, the index of the V->C list entry that is used (0 = most reliable).  Generated here:
+ * the all-zero configuration, single deviations 1..d1, pairs with (k-1)+(l-1) < d2, triples with
+ * total < d3, and the reference's hard-wired four-edge block (three of the four deviations sum to
+ * less than 2, the fourth is 1 or 2).  Ordered by cost = sum over deviating edges of
+ * (deviation + 3*edge), ties in generation order (the reference uses a stable insertion sort).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { float cost; int id; } cfg_key;
+
+int *nbgpu_build_config_table(int dc, int d1, int d2, int d3, int trunc, int *size_out)
+{
+    const int d4 = 2;
+    int a, b, c, e, x, y, z, w, n = 0, cap = 64;
+    int *tab = NULL;
+    *size_out = 0;
+    if (dc < 1 || dc > 16 || d1 < 0 || d2 < 0 || d3 < 0) return NULL;
+#define CFG_PUSH() do { if (n == cap || !tab) { cap *= 2; tab = realloc(tab, sizeof(int) * (size_t)cap * dc); if (!tab) return NULL; } \
+                        memset(tab + (size_t)n * dc, 0, sizeof(int) * dc); n++; } while (0)
+#define CFG(i) tab[(size_t)(n - 1) * dc + (i)]
+    CFG_PUSH();                                                     /* configuration 0: no deviation */
+    for (a = 0; a < dc; a++) for (x = 1; x <= d1; x++) { CFG_PUSH(); CFG(a) = x; }
+    for (a = 0; a < dc - 1; a++) for (b = a + 1; b < dc; b++)
+        for (x = 1; x <= d2; x++) for (y = 1; y <= d2; y++)
+            if (x + y - 2 < d2) { CFG_PUSH(); CFG(a) = x; CFG(b) = y; }
+    for (a = 0; a < dc - 2; a++) for (b = a + 1; b < dc - 1; b++) for (c = b + 1; c < dc; c++)
+        for (x = 1; x <= d3; x++) for (y = 1; y <= d3; y++) for (z = 1; z <= d3; z++)
+            if (x + y + z - 3 < d3) { CFG_PUSH(); CFG(a) = x; CFG(b) = y; CFG(c) = z; }
+    for (e = 0; e < dc - 3; e++) for (a = e + 1; a < dc - 2; a++) for (b = a + 1; b < dc - 1; b++) for (c = b + 1; c < dc; c++)
+        for (x = 1; x <= d4; x++) for (y = 1; y <= d4; y++) for (z = 1; z <= d4; z++) for (w = 1; w <= d4; w++)
+            if (x + y + z - 3 < d4) { CFG_PUSH(); CFG(a) = x; CFG(b) = y; CFG(c) = z; CFG(e) = w; }
+#undef CFG
+#undef CFG_PUSH
+    cfg_key *k = malloc(sizeof(cfg_key) * (size_t)n);
+    if (!k) { free(tab); return NULL; }
+    for (a = 0; a < n; a++) {
+        float cost = 0;
+        for (b = 0; b < dc; b++) if (tab[(size_t)a * dc + b] > 0) cost = cost + tab[(size_t)a * dc + b] + 3.0 * b;
+        k[a].cost = cost; k[a].id = a;
+    }
+    for (a = 1; a < n; a++) {                                       /* stable insertion sort, as sorting() :1315 */
+        cfg_key t = k[a];
+        for (b = a - 1; b >= 0 && k[b].cost > t.cost; b--) k[b + 1] = k[b];
+        k[b + 1] = t;
+    }
+    const int size = (trunc > 0 && trunc < n) ? trunc : n;
+    int *out = malloc(sizeof(int) * (size_t)size * dc);
+    if (out) for (a = 0; a < size; a++) memcpy(out + (size_t)a * dc, tab + (size_t)k[a].id * dc, sizeof(int) * dc);
+    free(k); free(tab);
+    if (out) *size_out = size;
+    return out;
+}
+
+/* public wrapper: copies the table into a caller buffer (NULL: only the size is returned) */
+int nbgpu_config_table(int dc, int d1, int d2, int d3, int trunc, int *table, int capacity)
+{
+    int size = 0;
+    int *t = nbgpu_build_config_table(dc, d1, d2, d3, trunc, &size);
+    if (!t) { nbgpu_set_global_error("cannot build the configuration table (dc=%d d=(%d,%d,%d))", dc, d1, d2, d3); return NBGPU_EINVAL; }
+    if (table) {
+        if (capacity < size) { free(t); nbgpu_set_global_error("configuration table needs %d rows, buffer has %d", size, capacity); return NBGPU_EINVAL; }
+        memcpy(table, t, sizeof(int) * (size_t)size * dc);
+    }
+    free(t);
+    return size;
+}

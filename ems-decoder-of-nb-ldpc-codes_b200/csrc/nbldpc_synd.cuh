@@ -1,0 +1,180 @@
+/*
+ * nbldpc_synd.cuh -- the syndrome-based check node on the GPU (sm_100a), one WARP per check node.
+ *
+ * Restates syndrome_ems (syndrome_decoder.c:26-284) with presorting_mvc (:289-496), sorting
+ * (:1315-1334) and bayes (:2142-2211):
+ *   1. presort: edges ascending by their 2nd-best LLR, then the first four by their 3rd-best LLR
+ *      (selection with strict '<': ties keep the lower index first);
+ *   2. one syndrome per configuration: LLR = f32 sum over the (presorted) edges of the list entry the
+ *      configuration names, GF = sum (XOR of binary images) of the entries' symbols;
+ *   3. STABLE sort of the syndromes by LLR -- the reference's insertion sort; here a stable LSD radix
+ *      sort of the f32 bit patterns (all LLRs are non-negative) with the configuration index as payload;
+ *   4. per edge d (presorted position): walk the sorted syndromes whose configuration does not deviate on
+ *      d ("decorrelation"), add the edge's best symbol, first hit of a symbol sets its LLR, later hits
+ *      go through bayes() in order; saturation at the LLR of decorrelated syndrome n_cv-1+3d, + offset.
+ * Symbols are binary images (GF addition == XOR) exactly as in the bubble path.
+ */
+#pragma once
+#include "nbldpc_device.cuh"
+
+#define NB_SYND_MAX 1024                 /* configurations per check node the shared-memory plan supports */
+
+/* a warp's shared memory for the syndrome check node, by shared-window address */
+struct SyndMem {
+    uint32_t lists;      /* dc lists: n_m f32 | n_m u8 (stride lstride) in ORIGINAL edge order        */
+    uint32_t key[2];     /* [Spad] u32 sort keys (ping-pong)                                           */
+    uint32_t pay[2];     /* [Spad] u16 configuration index (ping-pong)                                 */
+    uint32_t gf;         /* [Spad] u8 syndrome symbol, indexed by configuration                        */
+    uint32_t hist;       /* [256] u32                                                                   */
+    uint32_t M;          /* [256] f32 output LLRs of the current edge, indexed by binary image          */
+    uint32_t upd;        /* [256] u8  "symbol already has an LLR"                                       */
+    uint32_t perm;       /* [16] i32: original edge at presorted position i; [16] = sat of the current edge */
+    uint32_t cfg;        /* [S][dc] u8 configuration table (shared by the CTA)                          */
+    int lstride, n_m, dc, S, Spad, n_cv;
+};
+
+/* bayes(M1 = new LLR, M2 = current LLR), syndrome_decoder.c:2142-2211: double arguments and constants,
+ * float locals -- every conversion of the reference is reproduced. */
+__device__ __forceinline__ float synd_bayes(float m1f, float m2f)
+{
+    const double M1 = (double)m1f, M2 = (double)m2f;
+    float mn, dif;
+    if (M1 < M2) { mn = __double2float_rn(M1); dif = __double2float_rn(__dsub_rn(M2, M1)); }
+    else { mn = __double2float_rn(M2); dif = __double2float_rn(__dsub_rn(M1, M2)); }
+    const double d = (double)dif;
+    if (d < 0.1) mn = __double2float_rn(__dmul_rn(0.5, (double)mn));
+    else if (d < 0.2) mn = __double2float_rn(__dmul_rn(0.75, (double)mn));
+    else if (d < 1.0) mn = __double2float_rn(__dmul_rn(0.825, (double)mn));
+    else if (d < 2.0) mn = __double2float_rn(__dmul_rn(0.9375, (double)mn));
+    return mn;
+}
+
+/* steps 1-3: after this call key[0]/pay[0] hold the syndromes in the reference's sorted order */
+__device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
+{
+    const int dc = sm.dc, n_m = sm.n_m;
+    /* ---- presorting_mvc ---- */
+    {
+        const int i = lane < dc ? lane : 0;
+        const float k1 = lds_f32(sm.lists + i * sm.lstride + 4);                /* M_VtoC_LLR[i][1], :320 */
+        int rank = 0;
+        for (int j = 0; j < dc; j++) {
+            const float kj = __shfl_sync(NB_FULL, k1, j);
+            rank += (kj < k1 || (kj == k1 && j < i)) ? 1 : 0;
+        }
+        if (lane < dc) sts_u32(sm.perm + 4 * rank, (uint32_t)i);
+        __syncwarp();
+        /* first 'border' = 4 presorted edges again, by M_VtoC_LLR[.][2], :377-469 */
+        const int e = (int)lds_u32(sm.perm + 4 * (lane < 4 ? lane : 0));
+        const float k2 = lds_f32(sm.lists + e * sm.lstride + 8);
+        int rank2 = 0;
+        for (int j = 0; j < 4; j++) {
+            const float kj = __shfl_sync(NB_FULL, k2, j);
+            rank2 += (kj < k2 || (kj == k2 && j < lane)) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane < 4) sts_u32(sm.perm + 4 * rank2, (uint32_t)e);
+        __syncwarp();
+    }
+    /* ---- syndromes, :64-77 ---- */
+    for (int i = lane; i < sm.Spad; i += 32) {
+        uint32_t key = 0xffffffffu, gf = 0, pay = 0xffffu;
+        if (i < sm.S) {
+            float llr = 0.0f;
+            for (int j = 0; j < dc; j++) {
+                const uint32_t list = sm.lists + lds_u32(sm.perm + 4 * j) * sm.lstride;
+                const uint32_t c = lds_u8(sm.cfg + i * dc + j);
+                llr = __fadd_rn(llr, lds_f32(list + 4 * c));
+                gf ^= lds_u8(list + 4 * n_m + c);
+            }
+            key = __float_as_uint(llr); pay = (uint32_t)i;
+            sts_u8(sm.gf + i, gf);
+        }
+        sts_u32(sm.key[0] + 4 * i, key);
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[0] + 2 * i), "h"((unsigned short)pay) : "memory");
+    }
+    __syncwarp();
+    /* ---- stable LSD radix sort, 4 passes of 8 bits (sorting(), :1315-1334, is a stable insertion sort) ---- */
+    const unsigned lt = (1u << lane) - 1u;
+    for (int pass = 0; pass < 4; pass++) {
+        const int src = pass & 1, dst = src ^ 1, shift = 8 * pass;
+#pragma unroll
+        for (int b = 0; b < 8; b++) sts_u32(sm.hist + 4 * (lane * 8 + b), 0u);
+        __syncwarp();
+        for (int i = lane; i < sm.Spad; i += 32) {
+            const uint32_t d = (lds_u32(sm.key[src] + 4 * i) >> shift) & 255u;
+            const unsigned peers = __match_any_sync(NB_FULL, d);
+            if ((peers & lt) == 0) sts_u32(sm.hist + 4 * d, lds_u32(sm.hist + 4 * d) + __popc(peers));
+            __syncwarp();
+        }
+        /* exclusive prefix sum over the 256 bins: lane owns bins 8*lane .. 8*lane+7 */
+        uint32_t h[8], tot = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) { h[b] = lds_u32(sm.hist + 4 * (lane * 8 + b)); tot += h[b]; }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(NB_FULL, inc, o); if (lane >= o) inc += t; }
+        uint32_t run = inc - tot;
+#pragma unroll
+        for (int b = 0; b < 8; b++) { sts_u32(sm.hist + 4 * (lane * 8 + b), run); run += h[b]; }
+        __syncwarp();
+        for (int i = lane; i < sm.Spad; i += 32) {
+            const uint32_t k = lds_u32(sm.key[src] + 4 * i);
+            unsigned short p;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[src] + 2 * i));
+            const uint32_t d = (k >> shift) & 255u;
+            const unsigned peers = __match_any_sync(NB_FULL, d);
+            const uint32_t base = lds_u32(sm.hist + 4 * d);
+            const uint32_t pos = base + __popc(peers & lt);
+            sts_u32(sm.key[dst] + 4 * pos, k);
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[dst] + 2 * pos), "h"(p) : "memory");
+            __syncwarp();
+            if ((peers & lt) == 0) sts_u32(sm.hist + 4 * d, base + __popc(peers));
+            __syncwarp();
+        }
+    }
+}
+
+/* step 4 for presorted position d: on return M[256] (indexed by binary image of the rotated symbol)
+ * holds M_CtoV_LLR[d][.] after saturation (syndrome_decoder.c:93-209). */
+__device__ __forceinline__ void synd_edge(const SyndMem &sm, int d, float offset, int lane)
+{
+    const int dc = sm.dc;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int b = 0; b < 8; b++) { sts_f32(sm.M + 4 * (lane * 8 + b), 1500.0f); sts_u8(sm.upd + lane * 8 + b, 0u); }   /* :128-133 */
+    const uint32_t x = lds_u8(sm.lists + lds_u32(sm.perm + 4 * d) * sm.lstride + 4 * sm.n_m);   /* M_VtoC_GF[d][0], :103 */
+    const int target = sm.n_cv - 1 + 3 * d;                                                /* :195 */
+    int cnt = 0;
+    __syncwarp();
+    for (int i = lane; i < sm.Spad; i += 32) {
+        const float llr = __uint_as_float(lds_u32(sm.key[0] + 4 * i));
+        unsigned short p;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[0] + 2 * i));
+        const bool keep = (int)p < sm.S && lds_u8(sm.cfg + (int)p * dc + d) == 0;             /* :96-98 */
+        const unsigned bal = __ballot_sync(NB_FULL, keep);
+        if (bal == 0) continue;
+        const uint32_t g = keep ? (lds_u8(sm.gf + p) ^ x) : (0x100u + lane);
+        if (keep && cnt + __popc(bal & lt) == target) sts_f32(sm.perm + 64, llr);
+        cnt += __popc(bal);
+        const unsigned peers = __match_any_sync(NB_FULL, g);
+        const int rank = __popc(peers & lt);
+        const int rounds = __reduce_max_sync(NB_FULL, keep ? __popc(peers) : 0);
+        for (int r = 0; r < rounds; r++) {                                                  /* :138-164, in sorted order */
+            if (keep && rank == r) {
+                if (lds_u8(sm.upd + g)) sts_f32(sm.M + 4 * g, synd_bayes(llr, lds_f32(sm.M + 4 * g)));
+                else { sts_f32(sm.M + 4 * g, llr); sts_u8(sm.upd + g, 1u); }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    const float sat = lds_f32(sm.perm + 64);
+    const float hi = __fadd_rn(sat, offset);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {                                                           /* :198-209 */
+        const uint32_t a = sm.M + 4 * (lane * 8 + b);
+        if (lds_f32(a) > sat) sts_f32(a, hi);
+    }
+    __syncwarp();
+}

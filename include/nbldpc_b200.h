@@ -76,6 +76,11 @@ float nbgpu_sigma(const nbgpu_code *c, float EbN);                           /* 
 int nbgpu_awgn_bpsk_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin, float EbN,
                           float *noisy /*[N*logq]*/);                        /* channel.c:52-62 */
 
+/* Configuration table of the syndrome-based check node: replaces build_config_table + sort_config_table
+ * (syndrome_decoder.c:1542, 2285) and the truncation NB_LDPC.c:198-201.  Returns the number of
+ * configurations (rows of dc ints) or a negative error; table may be NULL to query the size. */
+int nbgpu_config_table(int dc, int d1, int d2, int d3, int trunc, int *table, int capacity);
+
 /* ------------------------------------------------------------------------------------------------
  * Device side
  * ---------------------------------------------------------------------------------------------- */
@@ -87,7 +92,9 @@ typedef struct {
     int   ecn_kind;     /* 0 = CheckPassLogEMS (L-Bubble F/B), 1 = syndrome_ems                    */
     int   early_stop;   /* 1 = stop a frame at the first zero syndrome (NB_LDPC.c:470); 0 = always
                            run nb_iter_max-1 passes (fixed-iteration throughput mode)               */
-    /* syndrome_ems only (NB_LDPC.c:189-201, all commented out there) */
+    /* syndrome_ems only (NB_LDPC.c:185-201, commented out there; see DESIGN.md "Syndrome path").
+       0 = default: d1 = n_m-1, d2 = min(15, n_m-1), d3 = min(5, n_m-1), cfg_trunc = 1000, n_cv = nb_oper
+       (NB_LDPC.c:185), border = 4 (syndrome_decoder.c:56; the only supported value) */
     int   d1, d2, d3, cfg_trunc, n_cv, border;
     /* tuning; 0 = automatic */
     int   frames_per_cta;  /* frames decoded together by one CTA                                  */

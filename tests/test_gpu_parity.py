@@ -124,18 +124,58 @@ def test_check_node_random(rel, n_m, nb_oper, offset):
     o.close(); d.close()
 
 
+def _synd_kw(g):
+    """Decoder keyword arguments of a fixture recorded with the reference's syndrome_ems as check node"""
+    if not g.synd_params:
+        return {}
+    d1, d2, d3, trunc, n_cv = g.synd_params
+    return dict(ecn_kind=1, d1=d1, d2=d2, d3=d3, cfg_trunc=trunc, n_cv=n_cv)
+
+
 @pytest.mark.parametrize("name", [n for n in golden_names() if "cn_node" in Golden(n).z])
 def test_check_node_on_reference_messages(name):
     g = Golden(name)
-    code, d = _dec(g.matrix, g.n_m, g.nb_oper, g.nb_iter_max, g.offset)
+    code, d = _dec(g.matrix, g.n_m, g.nb_oper, g.nb_iter_max, g.offset, **_synd_kw(g))
     z = g.z
     nodes = z["cn_node"]
     for node in np.unique(nodes):
         sel = np.nonzero(nodes == node)[0]
         cl, cg = d.check_node(int(node), z["cn_in_llr"][sel], z["cn_in_gf"][sel].astype(np.int32))
         assert cl.tobytes() == z["cn_out_llr"][sel].tobytes()
-        assert (cg == np.arange(g.GF)[None, None, :]).all()
+        if g.synd_params:
+            assert (cg == z["cn_out_gf"][sel]).all()
+        else:
+            assert (cg == np.arange(g.GF)[None, None, :]).all()
     d.close()
+
+
+@pytest.mark.parametrize("rel,n_m,dd,trunc,n_cv", [("matrices/Mat24_N480_M240", 16, (15, 10, 5), 0, 20),
+                                                   ("matrices/KN/N96_K48_GF256.txt", 20, (19, 15, 5), 1000, 25),
+                                                   ("matrices/N96_K48_GF64", 20, (19, 15, 5), 300, 25),
+                                                   ("synthetic/GF16_N24_M12_dc4", 12, (11, 5, 3), 0, 10),
+                                                   ("synthetic/GF64_N48_M16_dc6", 10, (9, 3, 2), 0, 8)])
+def test_syndrome_check_node_random(rel, n_m, dd, trunc, n_cv):
+    """syndrome_ems (presorting, syndromes, stable sort, decorrelation, bayes, saturation) on random lists incl. exact ties"""
+    code = nbldpc.Code(mpath(rel))
+    o = ol.Oracle(mpath(rel), code.dialect)
+    d = nbldpc.Decoder(code, n_m, 25, 10, 0.3, ecn_kind=1, d1=dd[0], d2=dd[1], d3=dd[2], cfg_trunc=trunc, n_cv=n_cv)
+    dc = int(code.row_deg[0])
+    cfg = o.build_config_table(dc, *dd, trunc)
+    assert (nbldpc.config_table(dc, *dd, trunc) == cfg).all()
+    rng = np.random.default_rng(5)
+    B = 96
+    vl = np.sort(rng.random((B, dc, n_m)).astype(np.float32) * rng.choice([1, 5, 20], (B, 1, 1)).astype(np.float32), axis=2)
+    vl[1::3] = np.round(vl[1::3] * 4) / 4                              # exact ties between syndromes
+    vl[:, :, 0] = 0
+    vl = np.sort(vl, axis=2).astype(np.float32)
+    vg = np.stack([np.stack([rng.permutation(code.q)[:n_m] for _ in range(dc)]) for _ in range(B)]).astype(np.int32)
+    for node in (0, code.M - 1):
+        cl, cg = d.check_node(node, vl, vg)
+        for b in range(B):
+            rl, rg = o.check_node_syndrome(node, vl[b], vg[b], n_m, cfg, 0.3, n_cv)
+            assert cl[b].tobytes() == rl.tobytes(), (node, b)
+            assert (cg[b] == rg).all(), (node, b)
+    o.close(); d.close()
 
 
 @pytest.mark.parametrize("q", [16, 64, 256])
@@ -177,7 +217,7 @@ def test_decode_equals_reference_run(name):
     fr, sigma = product_frames(code, g.nf, g.ebn)
     noisy = np.stack([f["noisy"] for f in fr])
     for nb_iter_max in sorted({g.nb_iter_max, 2, 4}):
-        d = nbldpc.Decoder(code, g.n_m, g.nb_oper, nb_iter_max, g.offset, max_batch=g.nf)
+        d = nbldpc.Decoder(code, g.n_m, g.nb_oper, nb_iter_max, g.offset, max_batch=g.nf, **_synd_kw(g))
         dec, synd, it = d.decode_noisy(noisy, sigma)
         for f in range(g.nf):
             rd, rs, ri, p = g.final(f, nb_iter_max)
@@ -221,6 +261,46 @@ def test_decode_batches_equal_oracle(rel, n_m, nb_oper, ebn, frames, early):
             assert app.tobytes() == r["app"].tobytes(), f
             assert ctov.tobytes() == r["ctov"].tobytes(), f
     o.close(); d.close()
+
+
+@pytest.mark.parametrize("rel,n_m,dd,trunc,n_cv,ebn,frames", [("matrices/N96_K48_GF64", 20, (19, 15, 5), 1000, 25, 2.0, 96),
+                                                              ("matrices/Mat24_N480_M240", 16, (15, 6, 3), 200, 12, 1.5, 16),
+                                                              ("synthetic/GF256_N24_M12_dc4", 20, (19, 15, 5), 1000, 25, 3.0, 24),
+                                                              ("synthetic/GF16_N24_M12_dc4", 12, (11, 5, 3), 0, 10, 3.0, 64)])
+def test_syndrome_decode_batches_equal_oracle(rel, n_m, dd, trunc, n_cv, ebn, frames):
+    """the whole decode loop with the syndrome-based check node (NB_LDPC.c:388 instead of :392)"""
+    code = nbldpc.Code(mpath(rel))
+    o = ol.Oracle(mpath(rel), code.dialect)
+    cfg = o.build_config_table(int(code.row_deg[0]), *dd, trunc)
+    fr, sigma = product_frames(code, frames, ebn)
+    noisy = np.stack([f["noisy"] for f in fr])
+    d = nbldpc.Decoder(code, n_m, 25, 10, 0.3, max_batch=frames, ecn_kind=1, d1=dd[0], d2=dd[1], d3=dd[2], cfg_trunc=trunc, n_cv=n_cv)
+    dec, synd, it = d.decode_noisy(noisy, sigma)
+    llr = d.channel(noisy, sigma)
+    for f in range(frames):
+        r = o.decode_frame(llr[f], n_m, 25, 10, 0.3, want_state=(f < 3), ecn=1, cfg=cfg, n_cv=n_cv)
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"] and it[f] == r["iters"], f
+        if "app" in r:
+            try:
+                app, ctov = d.get_state(f)
+            except nbldpc.NbgpuError as e:
+                assert e.code == nbldpc.ESTATE
+                continue
+            assert app.tobytes() == r["app"].tobytes() and ctov.tobytes() == r["ctov"].tobytes(), f
+    o.close(); d.close()
+
+
+def test_syndrome_parameter_errors():
+    code = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
+    for kw in (dict(d1=40), dict(n_cv=600), dict(border=3), dict(cfg_trunc=5000, d2=19, d3=19)):
+        with pytest.raises(nbldpc.NbgpuError) as e:
+            nbldpc.Decoder(code, 20, 25, 10, 0.3, ecn_kind=1, **kw)
+        assert e.value.code == nbldpc.EINVAL
+    code8 = nbldpc.Code(mpath("synthetic/GF16_N32_M8_dc8"))
+    d = nbldpc.Decoder(code8, 16, 25, 10, 0.3, ecn_kind=1, d1=15, d2=3, d3=2, n_cv=4)      # dc = 8 is accepted
+    d.close()
+    with pytest.raises(nbldpc.NbgpuError):
+        nbldpc.Decoder(nbldpc.Code(mpath("synthetic/GF64_N60_M12_dc10")), 14, 25, 10, 0.3, ecn_kind=1)
 
 
 def test_batch_shapes_and_errors():
