@@ -41,6 +41,10 @@ WORKLOADS = {
     "N96_K48_GF64": ("matrices/N96_K48_GF64", 20, 25, 0.3, 3.0, 1 << 20),
 }
 NB_ITER_MAX = 10
+# syndrome_ems parameters (d1, d2, d3, truncation, n_cv): the shapes of the commented call site NB_LDPC.c:185-201 with
+# d1 capped at n_m-1 (its d_1 = 40 overruns the n_m-wide message rows); see DESIGN.md "Syndrome path"
+SYND = {20: (19, 15, 5, 1000, 25), 16: (15, 15, 5, 1000, 25)}
+SYND_FRAMES = {"AD_64800_R12_GF256": 592, "MatDeclercq_R12_GF64": 592, "Mat24_N480_M240": 16384, "N96_K48_GF64": 1 << 18}
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
@@ -52,10 +56,12 @@ def find_matrix(rel):
     raise FileNotFoundError("%s not found under oracle/_ref (run __graft_entry__.build() where /root/reference exists)" % rel)
 
 
-def bytes_per_frame(N, E, q, n_m, passes):
+def bytes_per_frame(N, E, q, n_m, passes, ecn="bubble"):
     """Algorithmic HBM bytes of one frame (SURVEY.md 8d / DESIGN.md 4): dense f32 APP rows read+written once per edge
-    visit, lossless compressed CtoV read+written once per edge visit, intake write, decisions."""
-    return N * q * 4 + passes * E * (2 * q * 4 + 2 * min(q * 4, 5 * n_m + 4)) + N
+    visit, CtoV read+written once per edge visit (lossless record for the bubble check node, dense row for syndrome_ems
+    whose output is not a truncated list), intake write, decisions."""
+    ctov = q * 4 if ecn == "syndrome" else min(q * 4, 5 * n_m + 4)
+    return N * q * 4 + passes * E * (2 * q * 4 + 2 * ctov) + N
 
 
 def host_cores():
@@ -104,7 +110,7 @@ class ClockSampler:
 # -----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference main loop on the host cores
 # -----------------------------------------------------------------------------------------------------------------
-def run_reference_cpu(wl, frames_per_proc, procs, seconds_hint=None):
+def run_reference_cpu(wl, frames_per_proc, procs, seconds_hint=None, ecn="bubble"):
     """Runs `procs` concurrent copies of the reference (it is single-threaded; start.sh does the same) and returns
     (aggregate frames/s over decode time, kind, sample description, wall seconds)."""
     matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
@@ -119,6 +125,10 @@ def run_reference_cpu(wl, frames_per_proc, procs, seconds_hint=None):
                 env = dict(os.environ, NBREF_FORCE="1", NBREF_LEVEL="0", NBREF_DIALECT="ubs",
                            NBREF_SUMMARY=os.path.join(td, "sum%d.txt" % i))
                 env.pop("NBREF_TRACE", None)
+                env.pop("NBREF_ECN", None)
+                if ecn == "syndrome":
+                    env["NBREF_ECN"] = "syndrome"
+                    env["NBREF_SYND"] = ",".join(str(x) for x in SYND[n_m])
                 ps.append(subprocess.Popen([exe, str(frames_per_proc), str(NB_ITER_MAX), matrix, str(ebn), str(n_m), str(offset),
                                             str(nb_oper)], cwd=td, env=env, stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL,
                                            stderr=subprocess.DEVNULL))
@@ -132,15 +142,15 @@ def run_reference_cpu(wl, frames_per_proc, procs, seconds_hint=None):
                 assert int(passes) == int(fr) * (NB_ITER_MAX - 1), "reference did not run the fixed number of passes"
                 rate += int(fr) / float(dec_s)
                 nfr += int(fr)
-        sample = "%d concurrent single-thread runs of the unmodified reference main loop (oracle/_ref/essai_probe), %d frames each, " \
+        sample = "%d concurrent single-thread runs of the unmodified reference main loop (oracle/_ref/essai_probe%s), %d frames each, " \
                  "decode time only (channel return -> last Syndrom), Syndrom forced non-zero -> %d passes/frame" % (
-                     procs, frames_per_proc, NB_ITER_MAX - 1)
+                     procs, ", check node = the reference's syndrome_ems" if ecn == "syndrome" else "", frames_per_proc, NB_ITER_MAX - 1)
         return rate, "reference", sample, wall, nfr
     # fallback: the oracle port (plain-C restatement), same sampling
     import multiprocessing as mp
     t0 = time.time()
     with mp.Pool(procs) as pool:
-        res = pool.map(_port_worker, [(wl, frames_per_proc, i) for i in range(procs)])
+        res = pool.map(_port_worker, [(wl, frames_per_proc, i, ecn) for i in range(procs)])
     wall = time.time() - t0
     rate = sum(f / s for f, s in res)
     sample = "%d processes of the oracle port (oracle/liboracle.so), %d frames each, decode time only, %d passes/frame" % (
@@ -149,10 +159,14 @@ def run_reference_cpu(wl, frames_per_proc, procs, seconds_hint=None):
 
 
 def _port_worker(arg):
-    wl, frames, idx = arg
+    wl, frames, idx, ecn = arg
     import oracle_lib as ol
     matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
     o = ol.Oracle(find_matrix(matrix))
+    kw = {}
+    if ecn == "syndrome":
+        d1, d2, d3, trunc, n_cv = SYND[n_m]
+        kw = dict(ecn=1, cfg=o.build_config_table(int(o.row_deg[0]), d1, d2, d3, trunc), n_cv=n_cv)
     rng = np.random.default_rng(idx)
     sigma = o.sigma(ebn)
     tot = 0.0
@@ -160,15 +174,16 @@ def _port_worker(arg):
         noisy = (1.0 + sigma * rng.standard_normal((o.N, o.logGF))).astype(np.float32)
         llr = o.channel_llr(noisy, sigma)
         t0 = time.perf_counter()
-        o.decode_frame(llr, n_m, nb_oper, NB_ITER_MAX, offset, force=True)
+        o.decode_frame(llr, n_m, nb_oper, NB_ITER_MAX, offset, force=True, **kw)
         tot += time.perf_counter() - t0
     return frames, tot
 
 
-def cpu_sample_size(wl):
+def cpu_sample_size(wl, ecn="bubble"):
     """frames per process so that one concurrent batch is roughly 10-30 s of CPU work per core"""
-    return {"AD_64800_R12_GF256": 4, "Ahmed_64800_R34_GF16": 10, "MatDeclercq_R12_GF64": 10, "Mat24_N480_M240": 400,
-            "N96_K48_GF64": 10000}[wl]
+    n = {"AD_64800_R12_GF256": 4, "Ahmed_64800_R34_GF16": 10, "MatDeclercq_R12_GF64": 10, "Mat24_N480_M240": 400,
+         "N96_K48_GF64": 10000}[wl]
+    return max(1, n // 6) if ecn == "syndrome" else n
 
 
 def reference_arm(args, rank, world):
@@ -179,13 +194,13 @@ def reference_arm(args, rank, world):
     matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
     code = nbldpc.Code(find_matrix(matrix))
     cores = host_cores()
-    fpp = max(1, cpu_sample_size(wl) // 2)
+    fpp = max(1, cpu_sample_size(wl, args.ecn) // 2)
     for _ in range(min(args.warmup, 1)):
-        run_reference_cpu(wl, 1, cores)
+        run_reference_cpu(wl, 1, cores, ecn=args.ecn)
     rates, walls = [], []
     steps = max(1, min(args.steps, 3))
     for _ in range(steps):
-        rate, kind, sample, wall, nfr = run_reference_cpu(wl, fpp, cores)
+        rate, kind, sample, wall, nfr = run_reference_cpu(wl, fpp, cores, ecn=args.ecn)
         rates.append(rate); walls.append(wall)
     fps = statistics.mean(rates)
     val = fps * code.info_bits / 1e6
@@ -193,17 +208,21 @@ def reference_arm(args, rank, world):
             "unit": "Mbit/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * statistics.mean(walls),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (reference's own drand48 frame stream)",
             "frames_per_s": fps,
-            "config": config_dict(wl, code, fpp * cores, "host CPU only"),
+            "config": config_dict(wl, code, fpp * cores, "host CPU only", args.ecn),
             "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def config_dict(wl, code, frames, note):
+def config_dict(wl, code, frames, note, ecn="bubble"):
     matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
-    return {"workload": "%s: N=%d symbols over GF(%d) (%d code bits, %d info bits), M=%d, dc=%d, L-Bubble forward/backward EMS check node "
-                        "(CheckPassLogEMS), n_m=%d, nbOper=%d, offset=%.1f, NbIterMax=%d (= %d passes, early termination off), AWGN BPSK Eb/N0=%.1f dB"
-                        % (wl, code.N, code.q, code.N * code.logq, code.info_bits, code.M, code.dc_max, n_m, nb_oper, offset, NB_ITER_MAX,
+    if ecn == "syndrome":
+        cn = "syndrome-based check node (syndrome_ems with presorting, d=(%d,%d,%d), %d configurations max, n_cv=%d)" % SYND[n_m]
+    else:
+        cn = "L-Bubble forward/backward EMS check node (CheckPassLogEMS), nbOper=%d" % nb_oper
+    return {"workload": "%s: N=%d symbols over GF(%d) (%d code bits, %d info bits), M=%d, dc=%d, %s, n_m=%d, offset=%.1f, "
+                        "NbIterMax=%d (= %d passes, early termination off), AWGN BPSK Eb/N0=%.1f dB"
+                        % (wl, code.N, code.q, code.N * code.logq, code.info_bits, code.M, code.dc_max, cn, n_m, offset, NB_ITER_MAX,
                            NB_ITER_MAX - 1, ebn),
             "frames_per_step_per_gpu": frames, "cache": note}
 
@@ -241,11 +260,15 @@ def ours(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a B200: the product has no CPU fallback")
     wl = args.workload
     matrix, n_m, nb_oper, offset, ebn, dflt_B = WORKLOADS[wl]
-    B = args.frames or dflt_B
+    B = args.frames or (SYND_FRAMES.get(wl, dflt_B) if args.ecn == "syndrome" else dflt_B)
     code = nbldpc.Code(find_matrix(matrix))
     passes = NB_ITER_MAX - 1
+    kw = {}
+    if args.ecn == "syndrome":
+        d1, d2, d3, trunc, n_cv = SYND[n_m]
+        kw = dict(ecn_kind=1, d1=d1, d2=d2, d3=d3, cfg_trunc=trunc, n_cv=n_cv)
     dec = nbldpc.Decoder(code, n_m, nb_oper, NB_ITER_MAX, offset, early_stop=False, device=local_rank, max_batch=B,
-                         frames_per_cta=args.frames_per_cta, cns_per_step=args.cns_per_step)
+                         frames_per_cta=args.frames_per_cta, cns_per_step=args.cns_per_step, **kw)
     geo = dec.geometry()
     noisy, bits, sigma = synth_frames(code, B, ebn, rank)
     nbldpc.pin(noisy)
@@ -316,7 +339,7 @@ def ours(args, rank, local_rank, world):
 
     line = None
     if rank == 0:
-        bpf = bytes_per_frame(code.N, code.E, code.q, n_m, passes)
+        bpf = bytes_per_frame(code.N, code.E, code.q, n_m, passes, args.ecn)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -335,20 +358,20 @@ def ours(args, rank, local_rank, world):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (encoder codewords + numpy Gaussian noise at the reference's sigma)",
                 "frames_per_s": fps,
                 "config": config_dict(wl, code, B, "per-step working set %.1f GB and inputs %.0f MB per GPU, both larger than the 126 MB L2 (no explicit flush)"
-                                      % (geo["slots"] * (code.N * code.q * 4 + code.E * ((5 * n_m + 8 + 15) // 16 * 16)) / 1e9, noisy.nbytes / 1e6)),
+                                      % (geo["slots"] * (code.N * code.q * 4 + code.E * (code.q * 4 if args.ecn == "syndrome" else (5 * n_m + 8 + 15) // 16 * 16)) / 1e9, noisy.nbytes / 1e6), args.ecn),
                 "geometry": geo,
                 "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": int(noisy.nbytes), "d2h_bytes_per_step": int(sum(o.nbytes for o in out)),
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                             "kernel": "decode_kernel<%d>" % code.q, "kernel_ms": kernel_ms, "bytes_per_frame": bpf, "frames_per_launch": B},
+                             "kernel": "decode_kernel<%d, closed, %s>" % (code.q, "syndrome_ems" if args.ecn == "syndrome" else "CheckPassLogEMS"), "kernel_ms": kernel_ms, "bytes_per_frame": bpf, "frames_per_launch": B},
                 "clocks": clocks,
                 "counters": {"frames_per_step": int(counters[0]), "frames_nonzero_syndrome": int(counters[1]), "sum_iterations": int(counters[2]),
                              "slow_path_selects": dec.slow_selects()}}
         if world == 1 and not args.no_cpu:
             cores = host_cores()
-            rate, kind, sample, wall, nfr = run_reference_cpu(wl, cpu_sample_size(wl), cores)
+            rate, kind, sample, wall, nfr = run_reference_cpu(wl, cpu_sample_size(wl, args.ecn), cores, ecn=args.ecn)
             line["cpu_baseline"] = {"value": rate * code.info_bits / 1e6, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample,
                                     "frames_per_s": rate, "wall_s": wall}
         print(json.dumps(line), flush=True)
@@ -372,6 +395,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="AD_64800_R12_GF256", choices=sorted(WORKLOADS))
+    ap.add_argument("--ecn", default="bubble", choices=["bubble", "syndrome"],
+                    help="check node: bubble = CheckPassLogEMS (the reference's shipped hot path), syndrome = syndrome_ems")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (0 = workload default)")
     ap.add_argument("--frames-per-cta", type=int, default=0)
     ap.add_argument("--cns-per-step", type=int, default=0)
