@@ -331,11 +331,7 @@ def ours(args, rank, local_rank, world):
     # ---------------- counters: one NCCL all-reduce (the only collective of the path) ----------------
     bit_err = int((bits[:, :code.K, :] != np.stack([code_bits(code, d_res[:, k]) for k in range(code.K)], axis=1)).sum()) if args.count_errors else -1
     counters = np.array([B, int((s_res != 0).sum()), int(it_res.sum()), bit_err], np.int64)
-    if dist is not None:
-        import torch
-        t = torch.from_numpy(counters).cuda()
-        dist.all_reduce(t)
-        counters = t.cpu().numpy()
+    counters = nbldpc.multigpu.allreduce_counters(counters, device="cuda" if dist is not None else None)
 
     line = None
     if rank == 0:

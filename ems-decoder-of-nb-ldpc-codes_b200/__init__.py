@@ -388,6 +388,9 @@ def unpin(arr):
     _check(lib().nbgpu_host_unregister(C.c_void_p(arr.ctypes.data)))
 
 
+from . import multigpu  # noqa: E402,F401  (frame sharding over ranks; host logic only)
+
+
 def device_count():
     return int(lib().nbgpu_device_count())
 

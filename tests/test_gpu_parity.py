@@ -382,3 +382,48 @@ def test_full_size_round_trip_and_invariances(rel, n_m, ebn_hi):
     dec4, synd4, it4 = d.decode_noisy(noisy[:8], sigma)
     assert (dec4 == cw[:8]).all() and (synd4 == 0).all() and (it4 == 10).all()
     d.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Monte-Carlo statistics: the C driver (csrc/nbldpc_mc.c) and the sharded loop (multigpu.py) against the stock binary
+# ---------------------------------------------------------------------------------------------------
+KNOWN = [  # args of the reference binary, console (undetected, err frames, frames, bit errors, avr_it), frames in the results file
+    (["2000", "10", "matrices/N96_K48_GF64", "3.0", "20", "0.3", "25"], 0, (24, 2000, 153, "1.56"), 2001),
+    (["200", "10", "matrices/Mat24_N480_M240", "1.5", "16", "0.3", "25"], 0, (11, 200, 165, "6.23"), 201),
+    (["200", "10", "matrices/Mat24_N480_M240", "1.5", "20", "0.3", "25"], 1, (1, 200, 3, "5.30"), 201),      # syndrome_ems, SURVEY 8c
+]
+
+
+@pytest.mark.parametrize("args,ecn,console,nfile", KNOWN)
+def test_c_driver_reproduces_reference_console_and_results_file(args, ecn, console, nfile, tmp_path):
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(nbldpc.LIB_PATH), "nbldpc_mc")
+    assert os.path.exists(exe), "build the C driver with make -C <package>/csrc"
+    os.makedirs(tmp_path / "data")
+    a = list(args)
+    a[2] = matrix_path(a[2])
+    r = subprocess.run([exe] + a + ["128", "0", str(ecn)], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    m = re.findall(r"<(\d+)> FER=\s*(\d+)\s*/\s*(\d+)\s*=\s*[\d.]+\s*BER=\s*(\d+)\s*/\s*x\s*=\s*[\d.eE+-]+\s*avr_it=([\d.]+)", r.stdout)
+    assert m, r.stdout[-2000:]
+    last = m[-1]
+    assert (int(last[1]), int(last[2]), int(last[3]), last[4]) == console
+    files = list((tmp_path / "data").glob("results_*.txt"))
+    assert len(files) == 1
+    line = files[0].read_text()
+    mf = re.search(r"FER=\s*(\d+)\s*/\s*(\d+)", line)
+    assert (int(mf.group(1)), int(mf.group(2))) == (console[0], nfile), line
+
+
+def test_sharded_monte_carlo_on_the_gpu():
+    multigpu = __import__("importlib").import_module("ems-decoder-of-nb-ldpc-codes_b200.multigpu")
+    code = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
+    d = nbldpc.Decoder(code, 20, 25, 10, 0.3, max_batch=256)
+    st = multigpu.monte_carlo(code, 2000, 3.0, d.decode_noisy, batch=256)
+    assert (st["err_frames"], st["frames"], st["bit_errors"], st["frames_in_results_file"]) == (24, 2000, 153, 2001)
+    assert "%.2f" % (st["sum_it"] / st["frames"]) == "1.56"
+    # the two halves of a 2-rank run, computed one after the other, give the same per-frame rows
+    lo = multigpu.monte_carlo(code, 2000, 3.0, d.decode_noisy, batch=256, rank=0, world=1)
+    assert lo == st
+    d.close()

@@ -186,3 +186,17 @@ def test_schedule_preserves_reference_order(rel, cap, depth):
         cols = c.col[c.row_ptr[m]:c.row_ptr[m + 1]]
         assert (last[cols] < step_of[m]).all(), "check %d would run before/with an earlier check sharing a variable" % m
         last[cols] = step_of[m]
+
+
+def test_c_driver_is_built_and_fails_loudly_without_a_gpu(tmp_path):
+    """csrc/nbldpc_mc.c: the plain-C Monte-Carlo driver links against the C ABI only; without a GPU it reports the error of
+    nbgpu_create instead of decoding on the CPU"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(nbldpc.LIB_PATH), "nbldpc_mc")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode != 0 and "NbMonteCarlo" in r.stdout
+    if nbldpc.device_count() == 0:
+        r = subprocess.run([exe, "4", "10", matrix_path("matrices/N96_K48_GF64"), "3.0", "20", "0.3", "25"], cwd=tmp_path,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stdout
