@@ -39,6 +39,10 @@
 #define CTAS_PER_SM 2      /* resident CTAs per SM the decode kernel is compiled for (register cap 65536 / (NT_MAX * CTAS_PER_SM)) */
 #endif
 #define NE 2              /* edges interleaved per warp in phases 1 and 3 */
+#ifndef NB_PARK_MVC
+#define NB_PARK_MVC 1     /* 1: phase 1 parks the un-normalised Mvc row in the APP row for phase 3 (NB_LDPC.c:448 needs it);
+                             0: phase 3 recomputes it from APP and the old record (fewer bytes, more instructions) */
+#endif
 #define UNIT_NT 256       /* block size of the small unit-boundary kernels */
 
 struct KArgs {
@@ -331,19 +335,21 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                 for (int c = 0; c < cnt; c++) {
                     const int4 mt = wm.meta[c];
                     const int e0 = mt.x, dc = mt.y;
-                    const float *app_f = app + mt.z * frame_app;
+                    float *app_f = app + mt.z * frame_app;
                     const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
                     if (c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
                     for (int t = 0; t < dc; t += NE) {
                         float v[NE][VPL];
                         RecView r[NE];
                         int hv[NE];
+                        float *prow[NE];
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
                             const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));   /* t+e >= dc: duplicate of the last edge, result ignored */
                             const uint32_t ei = a.einfo[ed];
                             hv[e] = (ei >> 20) & 0xff;
-                            load_row<Q>(app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q), lane, v[e]);
+                            prow[e] = app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q);
+                            load_row<Q>(prow[e], lane, v[e]);
                             r[e] = load_record(ctov_f, ed, rl);
                         }
                         /* next pair of edges of the tile -> L2 while this pair is processed */
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                             expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
 #pragma unroll
                             for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
+                            if (NB_PARK_MVC && t + e < dc) store_row<Q>(prow[e], lane, v[e]);
                         }
                         float llr[NE]; int sym[NE];
                         select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
@@ -392,17 +399,19 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                         for (int e = 0; e < NE; e++) {
                             const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));
                             ei[e] = a.einfo[ed];
-                            load_row<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e]);
-                            r[e] = load_record(ctov_f, ed, rl);
+                            load_row<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e]);    /* parked Mvc, or APP */
+                            if (!NB_PARK_MVC) r[e] = load_record(ctov_f, ed, rl);
                         }
+                        if (!NB_PARK_MVC) {
 #pragma unroll
-                        for (int e = 0; e < NE; e++) {
-                            float cv[VPL];
-                            expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
+                            for (int e = 0; e < NE; e++) {
+                                float cv[VPL];
+                                expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
 #pragma unroll
-                            for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);          /* Mvc again, NB_LDPC.c:334 */
+                                for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* Mvc again, NB_LDPC.c:334 */
+                            }
+                            __syncwarp();                      /* every lane has consumed the old records */
                         }
-                        __syncwarp();                          /* every lane has consumed the old records */
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
                             if (t + e < dc) {

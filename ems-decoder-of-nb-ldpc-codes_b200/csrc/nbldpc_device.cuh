@@ -249,7 +249,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
     constexpr int LOGQ = QTraits<Q>::LOGQ;
     const bool active = (Q >= 32) || lane < Q;
     const int rounds = (n_m + 1 < Q) ? n_m + 1 : Q;
-    uint32_t head[NE], nkey[NE], nxt[NE], selp[NE];   /* head = smallest unpopped key of the lane, nkey = the one after it (register resident: no load on the REDUX chain) */
+    uint32_t head[NE], nxt[NE], selp[NE];
     bool bad[NE];
 #pragma unroll
     for (int e = 0; e < NE; e++) {
@@ -262,12 +262,10 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         sort_keys<VPL>(key);
         bad[e] = active && key[VPL - 1] >= 0x7f800000u;
 #pragma unroll
-        for (int j = 2; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
+        for (int j = 1; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
         scr[e][VPL * 32 + lane] = NB_KEY_INF;
-        scr[e][(VPL + 1) * 32 + lane] = NB_KEY_INF;
         head[e] = key[0];
-        nkey[e] = VPL > 1 ? key[VPL > 1 ? 1 : 0] : NB_KEY_INF;
-        nxt[e] = smem_u32(scr[e] + (VPL > 1 ? 64 : 32) + lane);
+        nxt[e] = smem_u32(scr[e] + 32 + lane);
         selp[e] = smem_u32(sel[e]);
     }
     /* no __syncwarp needed: every lane only reads back what it wrote itself */
@@ -277,14 +275,13 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                  ".reg .u32 m;\n\t"                                                                             \
                  "redux.sync.min.u32 m, %0, 0xffffffff;\n\t"                                                    \
                  "setp.eq.u32 p, %0, m;\n\t"                                                                    \
-                 "@p st.shared.u32 [%3+" #OFF "], %0;\n\t"                                                      \
-                 "@p mov.u32 %0, %1;\n\t"                                                                       \
-                 "@p ld.shared.u32 %1, [%2];\n\t"                                                               \
-                 "@p add.u32 %2, %2, 128;\n\t"                                                                  \
+                 "@p st.shared.u32 [%2+" #OFF "], %0;\n\t"                                                      \
+                 "@p ld.shared.u32 %0, [%1];\n\t"                                                               \
+                 "@p add.u32 %1, %1, 128;\n\t"                                                                  \
                  "}"                                                                                             \
-                 : "+r"(head[E]), "+r"(nkey[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
+                 : "+r"(head[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
     int r = 0;
-    for (; r + 4 <= rounds; r += 4) {
+    for (; r + 3 <= rounds; r += 3) {                 /* n_m + 1 = 21 rounds for the usual n_m = 20: no remainder */
 #pragma unroll
         for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
 #pragma unroll
@@ -292,9 +289,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
 #pragma unroll
         for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 8);
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 12);
-#pragma unroll
-        for (int e = 0; e < NE; e++) selp[e] += 16;
+        for (int e = 0; e < NE; e++) selp[e] += 12;
     }
     for (; r < rounds; r++) {
 #pragma unroll
