@@ -46,7 +46,7 @@
 #define UNIT_NT 256       /* block size of the small unit-boundary kernels */
 
 struct KArgs {
-    int N, M, E, q, logq, dc_max;
+    int N, M, E, q, logq, dc_max, dc_min;
     int n_m, nb_oper, passes, early_stop, nb_iter_max;
     float offset;
     int F, nw, cpw, cap, nsteps, L;     /* frames per group, warps per CTA, check nodes per warp, items per step, steps, lists per node */
@@ -66,21 +66,30 @@ struct KArgs {
     unsigned *queue, *slow_counter;
     /* shared memory map (bytes): tables | misc | per-warp scratch areas | per-warp lists */
     int off_tab, off_misc, off_wa, wa_bytes, off_wb, wb_bytes;
-    int wa_sel, wa_mask, wa_meta;       /* offsets inside a warp's scratch area (scr at 0) */
+    int wa_mask, wa_meta;               /* offsets inside a warp's small private area                                    */
+    int wb_scr1, wb_scr3, wb_U, wb_R;   /* offsets inside a warp's list area: phase-1 scratch (scr[NE] | sel[NE]), phase-3
+                                           scratch (scr[NE]), input lists U[cpw][dc_max], other lists R[cpw][L - dc_max].
+                                           Bubble path: the phase-1 scratch aliases R (unused until phase 2) and the phase-3
+                                           scratch aliases U (dead after phase 2).                                         */
     int lstride;                        /* bytes per list: n_m f32 | n_m u8 | len u8 | pad */
     int smem_bytes;
     /* syndrome-based check node (ecn = 1): dense CtoV rows, configuration table, per-warp sort buffers */
     int ecn, S, Spad, n_cv;
     const uint8_t *cfg;                 /* [S][dc_max] u8 */
     float *ctov_dense;                  /* [slots][E][q] f32 */
-    int off_cfg, sw_lists, sw_key, sw_pay, sw_gf, sw_hist, sw_M, sw_upd, sw_perm;   /* sw_*: offsets inside a warp's list area */
+    int off_cfg, sw_key, sw_pay, sw_gf, sw_hist, sw_M, sw_upd, sw_perm;   /* sw_*: offsets inside a warp's list area */
 };
 
 /* Lists of a warp's tile in shared memory, by 32-bit shared-window address.  c = check node of the
  * tile, li = list id.  One list = n_m f32 LLRs, n_m u8 symbols (binary images), 1 u8 length. */
 struct Lists {
-    uint32_t base; int lstride, cstride, n_m;
-    __device__ __forceinline__ uint32_t at(int c, int li) const { return base + c * cstride + li * lstride; }
+    uint32_t baseU, baseR; int lstride, strideU, strideR, n_m;     /* strides per check node */
+    /* li < dc: input list of edge li; li >= dc: forward/backward/merge list number li - dc */
+    __device__ __forceinline__ uint32_t at(int c, int li, int dc) const
+    {
+        return li < dc ? baseU + c * strideU + li * lstride : baseR + c * strideR + (li - dc) * lstride;
+    }
+    __device__ __forceinline__ uint32_t in(int c, int t) const { return baseU + c * strideU + t * lstride; }
     __device__ __forceinline__ uint32_t sym(uint32_t list) const { return list + 4 * n_m; }
     __device__ __forceinline__ uint32_t len(uint32_t list) const { return list + 5 * n_m; }
 };
@@ -99,23 +108,26 @@ __device__ __forceinline__ int id_out(int dc, int t)
 
 /* a warp's private shared memory */
 template <int Q> struct WarpMem {
-    uint32_t *scr[NE];       /* per in-flight edge: sorted keys / dense row               */
-    uint32_t *sel[NE];       /* winners of the selection rounds                            */
-    uint32_t mask;           /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided (shared address) */
-    int4 *meta;              /* [cpw] {first edge, degree (0 = skip), frame, -}            */
+    uint32_t *scr[NE];       /* phase 1, per in-flight edge: sorted keys / dense row                       */
+    uint32_t *sel[NE];       /* phase 1: winners of the selection rounds                                    */
+    uint32_t *scr3[NE];      /* phase 3, per in-flight edge: dense row                                      */
+    uint32_t mask;           /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided (shared address)  */
+    int4 *meta;              /* [cpw] {first edge, degree (0 = skip), frame, -}                             */
     Lists ls;
     __device__ __forceinline__ WarpMem(unsigned char *smem, const KArgs &a, int warp)
     {
         unsigned char *wa = smem + a.off_wa + warp * a.wa_bytes;
+        unsigned char *wb = smem + a.off_wb + warp * a.wb_bytes;
 #pragma unroll
         for (int e = 0; e < NE; e++) {
-            scr[e] = reinterpret_cast<uint32_t *>(wa) + e * QTraits<Q>::SCR_WORDS;
-            sel[e] = reinterpret_cast<uint32_t *>(wa + a.wa_sel) + e * 36;
+            scr[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + e * QTraits<Q>::SCR_WORDS;
+            sel[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + NE * QTraits<Q>::SCR_WORDS + e * 36;
+            scr3[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr3) + e * QTraits<Q>::SCR_WORDS;
         }
         mask = smem_u32(wa + a.wa_mask);
         meta = reinterpret_cast<int4 *>(wa + a.wa_meta);
-        ls.base = smem_u32(smem + a.off_wb + warp * a.wb_bytes);
-        ls.lstride = a.lstride; ls.cstride = a.L * a.lstride; ls.n_m = a.n_m;
+        ls.baseU = smem_u32(wb + a.wb_U); ls.baseR = smem_u32(wb + a.wb_R);
+        ls.lstride = a.lstride; ls.strideU = a.dc_max * a.lstride; ls.strideR = (a.L - a.dc_max) * a.lstride; ls.n_m = a.n_m;
     }
 };
 
@@ -142,7 +154,7 @@ __device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const int
                     a = id_F(dc, k); b = id_B(dc, dc - 3 - k); o = id_M(dc, k);
                 }
                 if (valid) {
-                    const uint32_t la = ls.at(c, a), lb = ls.at(c, b), lo = ls.at(c, o);
+                    const uint32_t la = ls.at(c, a, dc), lb = ls.at(c, b, dc), lo = ls.at(c, o, dc);
                     const int s = es_serial<Q>(la, ls.sym(la), (int)lds_u8(ls.len(la)), lb, ls.sym(lb), (int)lds_u8(ls.len(lb)),
                                                lo, ls.sym(lo), mask + 4 * lane, ls.n_m, nb_oper);
                     sts_u8(ls.len(lo), (uint32_t)s);
@@ -212,7 +224,7 @@ __device__ __forceinline__ SyndMem make_synd_mem(unsigned char *smem, const KArg
 {
     SyndMem sm;
     const uint32_t wb = smem_u32(smem + a.off_wb + warp * a.wb_bytes);
-    sm.lists = wb + a.sw_lists;
+    sm.lists = wb + a.wb_U;
     sm.key[0] = wb + a.sw_key; sm.key[1] = sm.key[0] + 4 * a.Spad;
     sm.pay[0] = wb + a.sw_pay; sm.pay[1] = sm.pay[0] + 2 * a.Spad;
     sm.gf = wb + a.sw_gf; sm.hist = wb + a.sw_hist; sm.M = wb + a.sw_M; sm.upd = wb + a.sw_upd; sm.perm = wb + a.sw_perm;
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
                             if (t + e < dc) {
-                                const uint32_t list = ls.at(c, t + e);
+                                const uint32_t list = ls.in(c, t + e);
                                 if (lane < n_m) {
                                     sts_f32(list + 4 * lane, llr[e]);
                                     sts_u8(ls.sym(list) + lane, (uint32_t)gf_rot_in<Q, CLOSED>(gf, sym[e], hv[e]));   /* bubble_decoder.c:145 */
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
 #pragma unroll
                             for (int e = 0; e < NE; e++) {
                                 float cv[VPL];
-                                expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
+                                expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr3[e]), cv);
 #pragma unroll
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* Mvc again, NB_LDPC.c:334 */
                             }
@@ -416,10 +428,10 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                         for (int e = 0; e < NE; e++) {
                             if (t + e < dc) {
                                 const uint32_t ed = (uint32_t)(e0 + t + e), var = ei[e] & 0xfffffu;
-                                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t + e)), (ei[e] >> 20) & 0xff, gf, a.offset, lane);
+                                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t + e), dc), (ei[e] >> 20) & 0xff, gf, a.offset, lane);
                                 store_record(ctov_f, ed, rl, nr, n_m, lane);
                                 float mcv[VPL];
-                                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr[e]), mcv);     /* :262-281 */
+                                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr3[e]), mcv);    /* :262-281 */
 #pragma unroll
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
                                 store_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v[e]);
@@ -589,7 +601,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
         for (int i = lane; i < cnt * dc * n_m; i += 32) {
             const int c = i / (dc * n_m), r = i - c * dc * n_m, t = r / n_m, k = r - t * n_m;
             const size_t src = ((size_t)(b0 + c) * dc + t) * n_m + k;
-            const uint32_t list = ls.at(c, t);
+            const uint32_t list = ls.in(c, t);
             sts_f32(list + 4 * k, vllr[src]);
             sts_u8(ls.sym(list) + k, (uint32_t)gf_rot_in<Q, CLOSED>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]));
             if (k == 0) sts_u8(ls.len(list), (uint32_t)n_m);
@@ -599,9 +611,9 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
         tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
         for (int c = 0; c < cnt; c++)
             for (int t = 0; t < dc; t++) {
-                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t)), a.hval[e0 + t], gf, a.offset, lane);
+                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t), dc), a.hval[e0 + t], gf, a.offset, lane);
                 float mcv[VPL];
-                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr[0]), mcv);
+                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr3[0]), mcv);
                 float *dst = cllr + ((size_t)(b0 + c) * dc + t) * Q;
                 store_row<Q>(dst, lane, mcv);
                 int *gdst = cgf + ((size_t)(b0 + c) * dc + t) * Q;
@@ -804,21 +816,27 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     int off = 0;
     k.off_tab = off; off += 512;
     k.off_misc = off; off += align_up((2 + 3 * k.F) * 4, 16);
-    /* per-warp scratch area: scr[NE] | sel[NE] | mask | meta */
-    int wa = NE * scr_words(k.q) * 4;
-    k.wa_sel = wa; wa += NE * 36 * 4;
-    k.wa_mask = 0;                       /* the ES 'seen' mask (q = 256: 1 KiB) aliases scr[0]: phases never overlap in a warp */
+    /* per-warp small area: ES mask (q = 256) | meta */
+    int wa = 0;
+    k.wa_mask = wa; wa += (k.q > 64 && k.ecn == 0) ? 8 * 32 * 4 : 0;
     k.wa_meta = wa; wa += cpw * 16;
     k.wa_bytes = align_up(wa, 16);
     k.off_wa = off; off += nw * k.wa_bytes;
-    /* per-warp lists: cpw nodes x L lists x {n_m f32 | n_m u8 | len u8} */
     k.lstride = align_up(5 * k.n_m + 1, 4);
-    k.wb_bytes = align_up(cpw * k.L * k.lstride, 16);
-    if (k.ecn == 1) {
-        /* syndrome check node: CTA-wide configuration table, then per warp: lists | keys x2 | payload x2 | gf | hist | M | upd | perm */
+    const int s3 = NE * scr_words(k.q) * 4, s1 = s3 + NE * 36 * 4;
+    if (k.ecn == 0) {
+        /* per-warp lists: U[cpw][dc_max] | R[cpw][L - dc_max], each list {n_m f32 | n_m u8 | len u8}.  Scratch aliases them. */
+        const int ub = align_up(std::max(cpw * k.dc_max * k.lstride, s3), 16);
+        const int rb = align_up(std::max(cpw * (k.L - k.dc_max) * k.lstride, s1), 16);
+        k.wb_U = 0; k.wb_scr3 = 0; k.wb_R = ub; k.wb_scr1 = ub;
+        k.wb_bytes = ub + rb;
+        if (k.dc_min < 3) { k.wb_scr3 = k.wb_bytes; k.wb_bytes += align_up(s3, 16); }   /* degree 2: the output lists ARE input lists */
+    } else {
+        /* syndrome check node: CTA-wide configuration table, then per warp: scratch | lists | keys x2 | payload x2 | gf | hist | M | upd | perm */
         k.off_cfg = off; off += align_up(k.S * k.dc_max, 16);
         int wb2 = 0;
-        k.sw_lists = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
+        k.wb_scr1 = wb2; k.wb_scr3 = wb2; wb2 += align_up(s1, 16);
+        k.wb_U = wb2; k.wb_R = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
         k.sw_key = wb2; wb2 += 2 * 4 * k.Spad;
         k.sw_pay = wb2; wb2 += 2 * 2 * k.Spad;
         k.sw_gf = wb2; wb2 += k.Spad;
@@ -863,7 +881,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     const int q = code->q, E = code->E, N = code->N, M = code->M;
     KArgs &k = c->k;
     memset(&k, 0, sizeof k);
-    k.N = N; k.M = M; k.E = E; k.q = q; k.logq = code->logq; k.dc_max = code->dc_max;
+    k.N = N; k.M = M; k.E = E; k.q = q; k.logq = code->logq; k.dc_max = code->dc_max; k.dc_min = code->dc_min;
     k.n_m = p->n_m; k.nb_oper = p->nb_oper; k.passes = p->nb_iter_max - 1; k.early_stop = p->early_stop;
     k.nb_iter_max = p->nb_iter_max; k.offset = p->offset;
     k.rec_stride = align_up(5 * p->n_m + 8, 16);
