@@ -246,7 +246,7 @@ __device__ __forceinline__ void synd_dense_row(const SyndMem &sm, const GFTab &g
 #pragma unroll
     for (int j = 0; j < QTraits<Q>::VPL; j++) {
         const int s = lane * QTraits<Q>::VPL + j;
-        mcv[j] = (Q >= 32 || lane < Q) ? lds_f32(sm.M + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)) : NB_SENT;
+        mcv[j] = (Q >= 32 || lane < Q) ? lds_f32(sm.hist + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)) : NB_SENT;
     }
 }
 
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_synd_kernel(const KArgs a
             float *dst = cllr + ((size_t)b * dc + t) * Q;
             int *gdst = cgf + ((size_t)b * dc + t) * Q;
             for (int k = lane; k < Q; k += 32) {
-                dst[k] = lds_f32(sm.M + 4 * gf.img[k]);
+                dst[k] = lds_f32(sm.hist + 4 * gf.img[k]);
                 gdst[k] = gf_rot_out<Q, CLOSED>(gf, gf.img[k], a.hval[e0 + t]);
             }
             __syncwarp();

@@ -25,9 +25,10 @@ struct SyndMem {
     uint32_t key[2];     /* [Spad] u32 sort keys (ping-pong)                                           */
     uint32_t pay[2];     /* [Spad] u16 configuration index (ping-pong)                                 */
     uint32_t gf;         /* [Spad] u8 syndrome symbol, indexed by configuration                        */
-    uint32_t hist;       /* [256] u32                                                                   */
-    uint32_t M;          /* [256] f32 output LLRs of the current edge, indexed by binary image          */
-    uint32_t upd;        /* [256] u8  "symbol already has an LLR"                                       */
+    uint32_t hist;       /* [256] u32 radix histogram; afterwards f32 output LLRs of the current edge,
+                            indexed by binary image                                                      */
+    uint32_t M;          /* [256] u32 first position of every symbol group in the symbol-grouped order    */
+    uint32_t upd;        /* (unused)                                                                     */
     uint32_t perm;       /* [16] i32: original edge at presorted position i; [16] = sat of the current edge */
     uint32_t cfg;        /* [S][dc] u8 configuration table (shared by the CTA)                          */
     int lstride, n_m, dc, S, Spad, n_cv;
@@ -47,6 +48,14 @@ __device__ __forceinline__ float synd_bayes(float m1f, float m2f)
     else if (d < 1.0) mn = __double2float_rn(__dmul_rn(0.825, (double)mn));
     else if (d < 2.0) mn = __double2float_rn(__dmul_rn(0.9375, (double)mn));
     return mn;
+}
+
+/* 5th radix pass: the digit is the syndrome's symbol (padding entries go to group 255 and sort last inside it) */
+__device__ __forceinline__ uint32_t synd_symbol_digit(const SyndMem &sm, int src, int i)
+{
+    unsigned short p;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[src] + 2 * i));
+    return (int)p < sm.S ? lds_u8(sm.gf + p) : 255u;
 }
 
 /* steps 1-3: after this call key[0]/pay[0] hold the syndromes in the reference's sorted order */
@@ -94,19 +103,22 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
         asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[0] + 2 * i), "h"((unsigned short)pay) : "memory");
     }
     __syncwarp();
-    /* ---- stable LSD radix sort, 4 passes of 8 bits (sorting(), :1315-1334, is a stable insertion sort) ---- */
+    /* ---- stable LSD radix sort, 4 passes of 8 bits over the f32 bit pattern (sorting(), :1315-1334, is a stable insertion
+     * sort), then a 5th stable pass on the syndrome's symbol: buffer 0 ends up in the reference's sorted order, buffer 1
+     * grouped by symbol with every group still ascending in (LLR, sorted position) ---- */
     const unsigned lt = (1u << lane) - 1u;
-    for (int pass = 0; pass < 4; pass++) {
+    for (int pass = 0; pass < 5; pass++) {
         const int src = pass & 1, dst = src ^ 1, shift = 8 * pass;
 #pragma unroll
         for (int b = 0; b < 8; b++) sts_u32(sm.hist + 4 * (lane * 8 + b), 0u);
         __syncwarp();
         for (int i = lane; i < sm.Spad; i += 32) {
-            const uint32_t d = (lds_u32(sm.key[src] + 4 * i) >> shift) & 255u;
-            const unsigned peers = __match_any_sync(NB_FULL, d);
-            if ((peers & lt) == 0) sts_u32(sm.hist + 4 * d, lds_u32(sm.hist + 4 * d) + __popc(peers));
-            __syncwarp();
+            uint32_t d;
+            if (pass < 4) d = (lds_u32(sm.key[src] + 4 * i) >> shift) & 255u;
+            else d = synd_symbol_digit(sm, src, i);
+            asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(sm.hist + 4 * d) : "memory");
         }
+        __syncwarp();
         /* exclusive prefix sum over the 256 bins: lane owns bins 8*lane .. 8*lane+7 */
         uint32_t h[8], tot = 0;
 #pragma unroll
@@ -117,64 +129,87 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
         uint32_t run = inc - tot;
 #pragma unroll
         for (int b = 0; b < 8; b++) { sts_u32(sm.hist + 4 * (lane * 8 + b), run); run += h[b]; }
+        if (pass == 4) {                                   /* group boundaries of the symbol-grouped order: start[256] + end */
+#pragma unroll
+            for (int b = 0; b < 8; b++) sts_u32(sm.M + 4 * (lane * 8 + b), lds_u32(sm.hist + 4 * (lane * 8 + b)));
+        }
         __syncwarp();
-        for (int i = lane; i < sm.Spad; i += 32) {
-            const uint32_t k = lds_u32(sm.key[src] + 4 * i);
-            unsigned short p;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[src] + 2 * i));
-            const uint32_t d = (k >> shift) & 255u;
-            const unsigned peers = __match_any_sync(NB_FULL, d);
-            const uint32_t base = lds_u32(sm.hist + 4 * d);
-            const uint32_t pos = base + __popc(peers & lt);
-            sts_u32(sm.key[dst] + 4 * pos, k);
-            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[dst] + 2 * pos), "h"(p) : "memory");
-            __syncwarp();
-            if ((peers & lt) == 0) sts_u32(sm.hist + 4 * d, base + __popc(peers));
-            __syncwarp();
+        /* stable scatter: two chunks of 32 per iteration so that two MATCH are in flight */
+        for (int i = lane; i < sm.Spad; i += 64) {
+            uint32_t k[2], d[2]; unsigned short p[2]; unsigned peers[2]; bool ok[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int ii = i + 32 * u;
+                ok[u] = ii < sm.Spad;
+                k[u] = ok[u] ? lds_u32(sm.key[src] + 4 * ii) : 0xffffffffu;
+                p[u] = 0xffff;
+                if (ok[u]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p[u]) : "r"(sm.pay[src] + 2 * ii));
+                d[u] = pass < 4 ? ((k[u] >> shift) & 255u) : (ok[u] ? synd_symbol_digit(sm, src, ii) : 255u);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) peers[u] = __match_any_sync(NB_FULL, d[u]);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (i - lane + 32 * u < sm.Spad) {          /* warp-uniform */
+                    const uint32_t base = lds_u32(sm.hist + 4 * d[u]);
+                    const uint32_t pos = base + __popc(peers[u] & lt);
+                    sts_u32(sm.key[dst] + 4 * pos, k[u]);
+                    asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[dst] + 2 * pos), "h"(p[u]) : "memory");
+                    __syncwarp();
+                    if ((peers[u] & lt) == 0) sts_u32(sm.hist + 4 * d[u], base + __popc(peers[u]));
+                    __syncwarp();
+                }
+            }
         }
     }
 }
 
-/* step 4 for presorted position d: on return M[256] (indexed by binary image of the rotated symbol)
- * holds M_CtoV_LLR[d][.] after saturation (syndrome_decoder.c:93-209). */
+/* step 4 for presorted position d: on return M'[256] (sm.hist, indexed by binary image of the rotated symbol) holds
+ * M_CtoV_LLR[d][.] after saturation (syndrome_decoder.c:93-209).  The reference walks the sorted syndromes and, per symbol,
+ * lets the first hit set the LLR and every later hit go through bayes(); hits of different symbols do not interact, so each
+ * lane replays the hits of its own eight symbols from the symbol-grouped copy (same order inside a symbol). */
 __device__ __forceinline__ void synd_edge(const SyndMem &sm, int d, float offset, int lane)
 {
     const int dc = sm.dc;
     const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int b = 0; b < 8; b++) { sts_f32(sm.M + 4 * (lane * 8 + b), 1500.0f); sts_u8(sm.upd + lane * 8 + b, 0u); }   /* :128-133 */
     const uint32_t x = lds_u8(sm.lists + lds_u32(sm.perm + 4 * d) * sm.lstride + 4 * sm.n_m);   /* M_VtoC_GF[d][0], :103 */
-    const int target = sm.n_cv - 1 + 3 * d;                                                /* :195 */
+    /* saturation level: LLR of decorrelated syndrome number n_cv-1+3d in the sorted order, :195 */
+    const int target = sm.n_cv - 1 + 3 * d;
+    float sat = 0.0f;
     int cnt = 0;
-    __syncwarp();
     for (int i = lane; i < sm.Spad; i += 32) {
-        const float llr = __uint_as_float(lds_u32(sm.key[0] + 4 * i));
         unsigned short p;
         asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[0] + 2 * i));
         const bool keep = (int)p < sm.S && lds_u8(sm.cfg + (int)p * dc + d) == 0;             /* :96-98 */
         const unsigned bal = __ballot_sync(NB_FULL, keep);
-        if (bal == 0) continue;
-        const uint32_t g = keep ? (lds_u8(sm.gf + p) ^ x) : (0x100u + lane);
-        if (keep && cnt + __popc(bal & lt) == target) sts_f32(sm.perm + 64, llr);
-        cnt += __popc(bal);
-        const unsigned peers = __match_any_sync(NB_FULL, g);
-        const int rank = __popc(peers & lt);
-        const int rounds = __reduce_max_sync(NB_FULL, keep ? __popc(peers) : 0);
-        for (int r = 0; r < rounds; r++) {                                                  /* :138-164, in sorted order */
-            if (keep && rank == r) {
-                if (lds_u8(sm.upd + g)) sts_f32(sm.M + 4 * g, synd_bayes(llr, lds_f32(sm.M + 4 * g)));
-                else { sts_f32(sm.M + 4 * g, llr); sts_u8(sm.upd + g, 1u); }
-            }
-            __syncwarp();
+        const int n = __popc(bal);
+        if (cnt + n > target) {
+            const bool mine = keep && cnt + __popc(bal & lt) == target;
+            const unsigned who = __ballot_sync(NB_FULL, mine);
+            sat = __shfl_sync(NB_FULL, __uint_as_float(lds_u32(sm.key[0] + 4 * i)), __ffs(who) - 1);
+            break;
         }
+        cnt += n;
     }
-    __syncwarp();
-    const float sat = lds_f32(sm.perm + 64);
     const float hi = __fadd_rn(sat, offset);
-#pragma unroll
-    for (int b = 0; b < 8; b++) {                                                           /* :198-209 */
-        const uint32_t a = sm.M + 4 * (lane * 8 + b);
-        if (lds_f32(a) > sat) sts_f32(a, hi);
+    /* per symbol: first hit sets, later hits through bayes, :128-164; then saturation, :198-209 */
+#pragma unroll 1
+    for (int b = 0; b < 8; b++) {
+        const int s = lane * 8 + b;                       /* output symbol (binary image) */
+        const uint32_t grp = (uint32_t)s ^ x;             /* syndromes with GF == grp land on s after adding the edge's best symbol */
+        const int lo = (int)lds_u32(sm.M + 4 * grp);
+        const int hi_i = grp == 255u ? sm.Spad : (int)lds_u32(sm.M + 4 * (grp + 1));
+        float m = 1500.0f;                                /* :131 */
+        bool upd = false;
+        for (int i = lo; i < hi_i; i++) {
+            unsigned short p;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[1] + 2 * i));
+            if ((int)p >= sm.S || lds_u8(sm.cfg + (int)p * dc + d) != 0) continue;
+            const float llr = __uint_as_float(lds_u32(sm.key[1] + 4 * i));
+            m = upd ? synd_bayes(llr, m) : llr;
+            upd = true;
+        }
+        sts_f32(sm.hist + 4 * s, m > sat ? hi : m);
     }
     __syncwarp();
 }
