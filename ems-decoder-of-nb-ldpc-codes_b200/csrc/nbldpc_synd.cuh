@@ -34,19 +34,23 @@ struct SyndMem {
     int lstride, n_m, dc, S, Spad, n_cv;
 };
 
-/* bayes(M1 = new LLR, M2 = current LLR), syndrome_decoder.c:2142-2211: double arguments and constants,
- * float locals -- every conversion of the reference is reproduced. */
-__device__ __forceinline__ float synd_bayes(float m1f, float m2f)
+/* bayes(M1 = new LLR, M2 = current LLR), syndrome_decoder.c:2142-2211.  The reference takes double arguments, keeps float
+ * locals and multiplies by double constants.  Bit-exact equivalents used here:
+ *   - M1 < M2 on doubles that are floats == the float comparison;
+ *   - dif = (float)(M2 - M1): the double difference is kept (one DADD), then rounded;
+ *   - (double)dif < 0.1 / 0.2 / 1 / 2  ==  dif < 0.1f / 0.2f / 1.0f / 2.0f  (0.1f and 0.2f are the first floats above 0.1, 0.2);
+ *   - (float)(c * (double)min) for c = 0.5, 0.75, 0.9375: the double product of a float by a 1-4 bit constant is exact, so its
+ *     rounding equals the float product; c = 0.825 is not representable and keeps the double multiplication. */
+__device__ __forceinline__ float synd_bayes(float m1, float m2)
 {
-    const double M1 = (double)m1f, M2 = (double)m2f;
-    float mn, dif;
-    if (M1 < M2) { mn = __double2float_rn(M1); dif = __double2float_rn(__dsub_rn(M2, M1)); }
-    else { mn = __double2float_rn(M2); dif = __double2float_rn(__dsub_rn(M1, M2)); }
-    const double d = (double)dif;
-    if (d < 0.1) mn = __double2float_rn(__dmul_rn(0.5, (double)mn));
-    else if (d < 0.2) mn = __double2float_rn(__dmul_rn(0.75, (double)mn));
-    else if (d < 1.0) mn = __double2float_rn(__dmul_rn(0.825, (double)mn));
-    else if (d < 2.0) mn = __double2float_rn(__dmul_rn(0.9375, (double)mn));
+    const bool lt = m1 < m2;
+    float mn = lt ? m1 : m2;
+    const float hi = lt ? m2 : m1;
+    const float dif = __double2float_rn(__dsub_rn((double)hi, (double)mn));
+    if (dif < 0.1f) mn = __fmul_rn(0.5f, mn);
+    else if (dif < 0.2f) mn = __fmul_rn(0.75f, mn);
+    else if (dif < 1.0f) mn = __double2float_rn(__dmul_rn(0.825, (double)mn));
+    else if (dif < 2.0f) mn = __fmul_rn(0.9375f, mn);
     return mn;
 }
 
@@ -192,24 +196,30 @@ __device__ __forceinline__ void synd_edge(const SyndMem &sm, int d, float offset
         cnt += n;
     }
     const float hi = __fadd_rn(sat, offset);
-    /* per symbol: first hit sets, later hits through bayes, :128-164; then saturation, :198-209 */
-#pragma unroll 1
-    for (int b = 0; b < 8; b++) {
-        const int s = lane * 8 + b;                       /* output symbol (binary image) */
-        const uint32_t grp = (uint32_t)s ^ x;             /* syndromes with GF == grp land on s after adding the edge's best symbol */
-        const int lo = (int)lds_u32(sm.M + 4 * grp);
-        const int hi_i = grp == 255u ? sm.Spad : (int)lds_u32(sm.M + 4 * (grp + 1));
-        float m = 1500.0f;                                /* :131 */
-        bool upd = false;
-        for (int i = lo; i < hi_i; i++) {
-            unsigned short p;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[1] + 2 * i));
-            if ((int)p >= sm.S || lds_u8(sm.cfg + (int)p * dc + d) != 0) continue;
-            const float llr = __uint_as_float(lds_u32(sm.key[1] + 4 * i));
-            m = upd ? synd_bayes(llr, m) : llr;
-            upd = true;
+    /* per symbol: first hit sets, later hits through bayes, :128-164; then saturation, :198-209.
+     * Lane L owns the output symbols 8L..8L+7; they receive the syndromes of the groups (8L+b)^x, i.e. of the eight
+     * CONSECUTIVE groups 8(L^(x>>3)) .. +7: one contiguous range of the symbol-grouped order, walked once. */
+    const uint32_t out = sm.hist + 4 * (lane * 8);
+#pragma unroll
+    for (int b = 0; b < 8; b++) sts_f32(out + 4 * b, hi);               /* symbols without a hit: 1500 > sat -> sat + offset */
+    const uint32_t g0 = ((uint32_t)lane ^ (x >> 3)) * 8u;
+    const int lo = (int)lds_u32(sm.M + 4 * g0);
+    const int hi_i = g0 + 8u >= 256u ? sm.Spad : (int)lds_u32(sm.M + 4 * (g0 + 8u));
+    int cur = -1;
+    float m = 0.0f;
+    for (int i = lo; i < hi_i; i++) {
+        unsigned short p;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[1] + 2 * i));
+        if ((int)p >= sm.S || lds_u8(sm.cfg + (int)p * dc + d) != 0) continue;
+        const int sy = (int)((lds_u8(sm.gf + p) ^ x) & 7u);
+        const float llr = __uint_as_float(lds_u32(sm.key[1] + 4 * i));
+        if (sy != cur) {
+            if (cur >= 0) sts_f32(out + 4 * cur, m > sat ? hi : m);
+            cur = sy; m = llr;
+        } else {
+            m = synd_bayes(llr, m);
         }
-        sts_f32(sm.hist + 4 * s, m > sat ? hi : m);
     }
+    if (cur >= 0) sts_f32(out + 4 * cur, m > sat ? hi : m);
     __syncwarp();
 }
