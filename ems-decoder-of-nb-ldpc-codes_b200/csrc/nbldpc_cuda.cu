@@ -50,7 +50,7 @@ struct KArgs {
     int n_m, nb_oper, passes, early_stop, nb_iter_max;
     float offset;
     int F, nw, cpw, cap, nsteps, L;     /* frames per group, warps per CTA, check nodes per warp, items per step, steps, lists per node */
-    int B, input_kind;                  /* 0 = noisy samples, 1 = dense LLR */
+    int B, input_kind, frame0;          /* frames of this launch; 0 = noisy samples, 1 = dense LLR; batch index of its first frame */
     double den;                         /* 2.0 * (double)(float)(sigma*sigma), channel.c:73 */
     const int *step_ptr, *isolated;
     int n_isolated;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
             for (size_t i = tid; i < (size_t)nf * frame_dense / 4; i += nthr) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         for (int i = tid; i < F; i += nthr) { s_done[i] = (i < nf) ? 0 : -1; s_synd[i] = 0; }
-        if (tid == 0) { *s_alive = nf; for (int f = 0; f < nf; f++) { a.frame_slot[base + f] = blockIdx.x * F + f; a.slot_frame[blockIdx.x * F + f] = base + f; } }
+        if (tid == 0) { *s_alive = nf; for (int f = 0; f < nf; f++) { a.frame_slot[base + f] = blockIdx.x * F + f; a.slot_frame[blockIdx.x * F + f] = a.frame0 + base + f; } }
         __syncthreads();
         /* variables that no check node touches keep their channel decision */
         for (int w = warp; w < nf * a.n_isolated; w += nw) {
@@ -752,8 +752,8 @@ static const void *checknode_fn(int q, int closed, int ecn)
  * ---------------------------------------------------------------------------------------------- */
 struct nbgpu_ctx {
     int device;
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1, ev_t0, ev_t1;
+    cudaStream_t stream, copy_stream;        /* kernels | host<->device copies of the chunked end-to-end path */
+    cudaEvent_t ev0, ev1, ev_t0, ev_t1, ev_h2d[4], ev_k[4];
     int per_sm;
     nbgpu_params p;
     KArgs k;
@@ -875,6 +875,8 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     CK(c, cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { ctx_err(c, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); free(c); return NBGPU_ECUDA; }
     CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) { CK(c, cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming)); CK(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)); }
     CK(c, cudaEventCreate(&c->ev0)); CK(c, cudaEventCreate(&c->ev1));
     CK(c, cudaEventCreate(&c->ev_t0)); CK(c, cudaEventCreate(&c->ev_t1));
 
@@ -1012,9 +1014,9 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     CK(c, cudaMalloc((void **)&c->d_frame_slot, (size_t)max_batch * sizeof(int)));
     CK(c, cudaMalloc((void **)&c->d_slot_frame, (size_t)c->nslots * sizeof(int)));
     CK(c, cudaMemset(c->d_slot_frame, 0xff, (size_t)c->nslots * sizeof(int)));
-    CK(c, cudaMalloc((void **)&c->d_queue, 2 * sizeof(unsigned)));
-    c->d_slow = c->d_queue + 1;
-    CK(c, cudaMemset(c->d_queue, 0, 2 * sizeof(unsigned)));
+    CK(c, cudaMalloc((void **)&c->d_queue, 8 * sizeof(unsigned)));       /* [0..3] work queues of up to 4 chunks, [4] slow-path counter */
+    c->d_slow = c->d_queue + 4;
+    CK(c, cudaMemset(c->d_queue, 0, 8 * sizeof(unsigned)));
     k.app = c->d_app; k.ctov = c->d_ctov; k.dec = c->d_dec; k.ctov_dense = c->d_ctov_dense;
     k.out_decide = c->d_decide; k.out_synd = c->d_synd; k.out_iters = c->d_iters;
     k.frame_slot = c->d_frame_slot; k.slot_frame = c->d_slot_frame; k.queue = c->d_queue; k.slow_counter = c->d_slow;
@@ -1034,6 +1036,8 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    for (int i = 0; i < 4; i++) { if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     free(c->row_ptr_h); free(c->inv_h);
     free(c);
@@ -1166,17 +1170,70 @@ extern "C" int nbgpu_download(nbgpu_ctx *c, int *decide, int *synd, int *iters)
     return NBGPU_OK;
 }
 
+/* End-to-end decode of B frames from HOST buffers.  Large batches are cut into up to four chunks so that the H2D copy of
+ * chunk i+1 and the D2H copy of chunk i-1 run (on the copy stream) under the kernel of chunk i; every chunk still fills
+ * the persistent grid at least twice.  Small batches take the single-launch path (and keep their state readable). */
+static int decode_host(nbgpu_ctx *c, const float *src, size_t per_frame, int kind, int B, int *decide, int *synd, int *iters)
+{
+    if (!c || !src) { ctx_err(c, "NULL argument"); return NBGPU_EINVAL; }
+    if (B < 1 || B > c->max_batch) { ctx_err(c, "B=%d outside 1..max_batch=%d", B, c->max_batch); return NBGPU_EINVAL; }
+    const int wave = c->grid * c->k.F;
+    int nch = B / (2 * wave);
+    nch = nch < 1 ? 1 : nch > 4 ? 4 : nch;
+    if (getenv("NBGPU_NO_CHUNKS")) nch = 1;
+    if (nch == 1) {
+        int rc = upload_common(c, src, per_frame, B, kind);
+        if (rc || (rc = nbgpu_run(c)) || (rc = nbgpu_download(c, decide, synd, iters))) return rc;
+        return NBGPU_OK;
+    }
+    CK(c, cudaSetDevice(c->device));
+    int rc = ensure_input(c, per_frame * (size_t)c->max_batch);
+    if (rc) return rc;
+    c->resident_B = B; c->resident_kind = kind;
+    int lo[5];
+    for (int i = 0; i <= nch; i++) lo[i] = (int)(((long)B * i / nch) / c->k.F * c->k.F);
+    lo[nch] = B;
+    CK(c, cudaStreamSynchronize(c->stream));                  /* earlier work on the buffers is done */
+    for (int i = 0; i < nch; i++) {
+        CK(c, cudaMemcpyAsync(c->d_in + per_frame * lo[i], src + per_frame * lo[i], per_frame * (lo[i + 1] - lo[i]) * sizeof(float),
+                              cudaMemcpyHostToDevice, c->copy_stream));
+        CK(c, cudaEventRecord(c->ev_h2d[i], c->copy_stream));
+    }
+    CK(c, cudaMemsetAsync(c->d_queue, 0, 4 * sizeof(unsigned), c->stream));
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < nch; i++) {
+        KArgs k = c->k;
+        const int n = lo[i + 1] - lo[i];
+        k.B = n; k.input_kind = kind; k.in = c->d_in + per_frame * lo[i];
+        k.out_decide = c->d_decide + (size_t)lo[i] * c->N; k.out_synd = c->d_synd + lo[i]; k.out_iters = c->d_iters + lo[i];
+        k.frame_slot = c->d_frame_slot + lo[i]; k.queue = c->d_queue + i; k.frame0 = lo[i];
+        const int grid = std::min(c->grid, (n + k.F - 1) / k.F);
+        CK(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[i], 0));
+        void *args[] = { (void *)&k };
+        CK(c, cudaLaunchKernel(decode_fn(c->q, k.gf_closed, k.ecn), dim3(grid), dim3(k.nw * 32), args, k.smem_bytes, c->stream));
+        CK(c, cudaEventRecord(c->ev_k[i], c->stream));
+        c->launches += 1;
+        CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_k[i], 0));
+        if (decide) CK(c, cudaMemcpyAsync(decide + (size_t)lo[i] * c->N, c->d_decide + (size_t)lo[i] * c->N, (size_t)n * c->N * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+        if (synd) CK(c, cudaMemcpyAsync(synd + lo[i], c->d_synd + lo[i], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+        if (iters) CK(c, cudaMemcpyAsync(iters + lo[i], c->d_iters + lo[i], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CK(c, cudaEventRecord(c->ev1, c->stream));
+    CK(c, cudaStreamSynchronize(c->copy_stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return NBGPU_OK;
+}
+
 extern "C" int nbgpu_decode_noisy(nbgpu_ctx *c, const float *noisy, float sigma, int B, int *decide, int *synd, int *iters)
 {
-    int rc;
-    if ((rc = nbgpu_upload_noisy(c, noisy, sigma, B)) || (rc = nbgpu_run(c)) || (rc = nbgpu_download(c, decide, synd, iters))) return rc;
-    return NBGPU_OK;
+    if (!c) return NBGPU_EINVAL;
+    c->k.den = 2.0 * (double)(float)(sigma * sigma);                      /* 2.0*SQR(sigma), channel.c:73 */
+    return decode_host(c, noisy, (size_t)c->N * c->logq, 0, B, decide, synd, iters);
 }
 extern "C" int nbgpu_decode_llr(nbgpu_ctx *c, const float *llr, int B, int *decide, int *synd, int *iters)
 {
-    int rc;
-    if ((rc = nbgpu_upload_llr(c, llr, B)) || (rc = nbgpu_run(c)) || (rc = nbgpu_download(c, decide, synd, iters))) return rc;
-    return NBGPU_OK;
+    if (!c) return NBGPU_EINVAL;
+    return decode_host(c, llr, (size_t)c->N * c->q, 1, B, decide, synd, iters);
 }
 
 extern "C" int nbgpu_get_state(nbgpu_ctx *c, int frame, float *APP, float *CtoV)

@@ -303,6 +303,36 @@ def test_syndrome_parameter_errors():
         nbldpc.Decoder(nbldpc.Code(mpath("synthetic/GF64_N60_M12_dc10")), 14, 25, 10, 0.3, ecn_kind=1)
 
 
+def test_chunked_end_to_end_path_equals_single_launch():
+    """nbgpu_decode_noisy cuts large batches into chunks whose copies overlap the kernels; the results must not depend on it"""
+    code = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
+    d = nbldpc.Decoder(code, 20, 25, 10, 0.3, max_batch=1 << 17)
+    geo = d.geometry()
+    B = 5 * geo["grid"] * geo["frames_per_cta"] + 37                    # at least two chunks, ragged tail
+    assert B <= 1 << 17
+    fr, sigma = product_frames(code, 64, 2.5)
+    rng = np.random.default_rng(3)
+    noisy = np.stack([f["noisy"] for f in fr])[rng.integers(0, 64, B)]
+    noisy += (rng.standard_normal(noisy.shape) * 0.05).astype(np.float32)
+    l0 = d.launch_count()
+    a = d.decode_noisy(noisy, sigma)
+    assert d.launch_count() - l0 >= 2, "the batch was not chunked"
+    os.environ["NBGPU_NO_CHUNKS"] = "1"
+    try:
+        l0 = d.launch_count()
+        b = d.decode_noisy(noisy, sigma)
+        assert d.launch_count() - l0 == 1
+    finally:
+        del os.environ["NBGPU_NO_CHUNKS"]
+    for x, y in zip(a, b):
+        assert (x == y).all()
+    o = ol.Oracle(matrix_path("matrices/N96_K48_GF64"))
+    for f in (0, B // 2, B - 1):
+        r = o.decode_frame(o.channel_llr(noisy[f], sigma), 20, 25, 10, 0.3)
+        assert (a[0][f] == r["decide"]).all() and a[1][f] == r["synd"] and a[2][f] == r["iters"]
+    o.close(); d.close()
+
+
 def test_batch_shapes_and_errors():
     code = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
     fr, sigma = product_frames(code, 37, 2.5)
