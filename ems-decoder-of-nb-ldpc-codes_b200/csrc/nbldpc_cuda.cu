@@ -39,10 +39,7 @@
 #define CTAS_PER_SM 2      /* resident CTAs per SM the decode kernel is compiled for (register cap 65536 / (NT_MAX * CTAS_PER_SM)) */
 #endif
 #define NE 2              /* edges interleaved per warp in phases 1 and 3 */
-#ifndef NB_PARK_MVC
-#define NB_PARK_MVC 1     /* 1: phase 1 parks the un-normalised Mvc row in the APP row for phase 3 (NB_LDPC.c:448 needs it);
-                             0: phase 3 recomputes it from APP and the old record (fewer bytes, more instructions) */
-#endif
+
 #define UNIT_NT 256       /* block size of the small unit-boundary kernels */
 
 struct KArgs {
@@ -66,7 +63,7 @@ struct KArgs {
     unsigned *queue, *slow_counter;
     /* shared memory map (bytes): tables | misc | per-warp scratch areas | per-warp lists */
     int off_tab, off_misc, off_wa, wa_bytes, off_wb, wb_bytes;
-    int wa_mask, wa_meta;               /* offsets inside a warp's small private area                                    */
+    int wa_mask, wa_meta, wa_einfo;     /* offsets inside a warp's small private area: ES mask | tile meta | tile edge words */
     int wb_scr1, wb_scr3, wb_U, wb_R;   /* offsets inside a warp's list area: phase-1 scratch (scr[NE] | sel[NE]), phase-3
                                            scratch (scr[NE]), input lists U[cpw][dc_max], other lists R[cpw][L - dc_max].
                                            Bubble path: the phase-1 scratch aliases R (unused until phase 2) and the phase-3
@@ -106,13 +103,21 @@ __device__ __forceinline__ int id_out(int dc, int t)
     return id_M(dc, t - 1);
 }
 
+/* tile description in shared memory: per check node {first edge | degree << 24, frame}; reads come back as int4 {e0, dc, f, 0} */
+struct TileMeta {
+    int2 *p;
+    __device__ __forceinline__ int4 operator[](int c) const { const int2 m = p[c]; return make_int4(m.x & 0xffffff, (int)((unsigned)m.x >> 24), m.y, 0); }
+    __device__ __forceinline__ void set(int c, int e0, int dc, int f) const { p[c] = make_int2(e0 | (dc << 24), f); }
+};
+
 /* a warp's private shared memory */
 template <int Q> struct WarpMem {
     uint32_t *scr[NE];       /* phase 1, per in-flight edge: sorted keys / dense row                       */
     uint32_t *sel[NE];       /* phase 1: winners of the selection rounds                                    */
     uint32_t *scr3[NE];      /* phase 3, per in-flight edge: dense row                                      */
     uint32_t mask;           /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided (shared address)  */
-    int4 *meta;              /* [cpw] {first edge, degree (0 = skip), frame, -}                             */
+    TileMeta meta;           /* [cpw] {first edge | degree << 24 (0 = skip), frame}                         */
+    uint32_t *ew;            /* [cpw][dc_max] einfo words of the tile's edges (one coalesced load per tile) */
     Lists ls;
     __device__ __forceinline__ WarpMem(unsigned char *smem, const KArgs &a, int warp)
     {
@@ -125,7 +130,8 @@ template <int Q> struct WarpMem {
             scr3[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr3) + e * QTraits<Q>::SCR_WORDS;
         }
         mask = smem_u32(wa + a.wa_mask);
-        meta = reinterpret_cast<int4 *>(wa + a.wa_meta);
+        meta.p = reinterpret_cast<int2 *>(wa + a.wa_meta);
+        ew = reinterpret_cast<uint32_t *>(wa + a.wa_einfo);
         ls.baseU = smem_u32(wb + a.wb_U); ls.baseR = smem_u32(wb + a.wb_R);
         ls.lstride = a.lstride; ls.strideU = a.dc_max * a.lstride; ls.strideR = (a.L - a.dc_max) * a.lstride; ls.n_m = a.n_m;
     }
@@ -136,7 +142,7 @@ template <int Q> struct WarpMem {
  * Slots 2/3: the merges ES(F_k, B_{dc-3-k}) (:217-227) whose later input appears in round r-1:
  * k = r-1 (if k >= dc-3-k) and k = dc-2-r (if dc-3-k = r-1 > k). */
 template <int Q>
-__device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const int4 *meta, int cnt, int dcmax, uint32_t mask,
+__device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const TileMeta &meta, int cnt, int dcmax, uint32_t mask,
                                                       int lane, int nb_oper)
 {
     for (int r = 1; r <= dcmax - 2; r++) {
@@ -339,7 +345,13 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                 if (lane < cnt) {
                     const int item = first + lane, f = item / ncn;
                     const uint32_t info = a.cninfo[c0 + item - f * ncn];
-                    wm.meta[lane] = make_int4(info & 0xffffff, s_done[f] ? 0 : (int)(info >> 24), f, 0);
+                    wm.meta.set(lane, info & 0xffffff, s_done[f] ? 0 : (int)(info >> 24), f);
+                }
+                __syncwarp();
+                for (int i = lane; i < cnt * dcm; i += 32) {   /* edge words of the tile: variable | coefficient | last-visit flag */
+                    const int c = i / dcm, t = i - c * dcm;
+                    const int4 mt = wm.meta[c];
+                    if (t < mt.y) wm.ew[i] = a.einfo[mt.x + t];
                 }
                 __syncwarp();
                 if constexpr (ECN == 0) {
@@ -357,8 +369,9 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                         float *prow[NE];
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
-                            const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));   /* t+e >= dc: duplicate of the last edge, result ignored */
-                            const uint32_t ei = a.einfo[ed];
+                            const int te = min(t + e, dc - 1);                 /* t+e >= dc: duplicate of the last edge, result ignored */
+                            const uint32_t ed = (uint32_t)(e0 + te);
+                            const uint32_t ei = wm.ew[c * dcm + te];
                             hv[e] = (ei >> 20) & 0xff;
                             prow[e] = app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q);
                             load_row<Q>(prow[e], lane, v[e]);
@@ -376,7 +389,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                             expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
 #pragma unroll
                             for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
-                            if (NB_PARK_MVC && t + e < dc) store_row<Q>(prow[e], lane, v[e]);
+                            if (t + e < dc) store_row<Q>(prow[e], lane, v[e]);     /* parked for phase 3 (NB_LDPC.c:448 adds this vector) */
                         }
                         float llr[NE]; int sym[NE];
                         select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
@@ -405,24 +418,11 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                     uint8_t *dec_f = dec + mt.z * N;
                     for (int t = 0; t < dc; t += NE) {
                         float v[NE][VPL];
-                        RecView r[NE];
                         uint32_t ei[NE];
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
-                            const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));
-                            ei[e] = a.einfo[ed];
-                            load_row<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e]);    /* parked Mvc, or APP */
-                            if (!NB_PARK_MVC) r[e] = load_record(ctov_f, ed, rl);
-                        }
-                        if (!NB_PARK_MVC) {
-#pragma unroll
-                            for (int e = 0; e < NE; e++) {
-                                float cv[VPL];
-                                expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr3[e]), cv);
-#pragma unroll
-                                for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* Mvc again, NB_LDPC.c:334 */
-                            }
-                            __syncwarp();                      /* every lane has consumed the old records */
+                            ei[e] = wm.ew[c * dcm + min(t + e, dc - 1)];
+                            load_row<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e]);    /* the Mvc row parked by phase 1 */
                         }
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
@@ -459,8 +459,9 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                             int hv[NE];
 #pragma unroll
                             for (int e = 0; e < NE; e++) {
-                                const uint32_t ed = (uint32_t)(e0 + min(t + e, dc - 1));
-                                const uint32_t ei = a.einfo[ed];
+                                const int te = min(t + e, dc - 1);
+                                const uint32_t ed = (uint32_t)(e0 + te);
+                                const uint32_t ei = wm.ew[c * dcm + te];
                                 hv[e] = (ei >> 20) & 0xff;
                                 float cv[VPL];
                                 load_row<Q>(app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q), lane, v[e]);
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
             sts_u8(ls.sym(list) + k, (uint32_t)gf_rot_in<Q, CLOSED>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]));
             if (k == 0) sts_u8(ls.len(list), (uint32_t)n_m);
         }
-        if (lane < cnt) wm.meta[lane] = make_int4(e0, dc, 0, 0);
+        if (lane < cnt) wm.meta.set(lane, e0, dc, 0);
         __syncwarp();
         tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
         for (int c = 0; c < cnt; c++)
@@ -819,7 +820,8 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     /* per-warp small area: ES mask (q = 256) | meta */
     int wa = 0;
     k.wa_mask = wa; wa += (k.q > 64 && k.ecn == 0) ? 8 * 32 * 4 : 0;
-    k.wa_meta = wa; wa += cpw * 16;
+    k.wa_meta = wa; wa += cpw * 8;
+    k.wa_einfo = wa; wa += cpw * k.dc_max * 4;
     k.wa_bytes = align_up(wa, 16);
     k.off_wa = off; off += nw * k.wa_bytes;
     k.lstride = align_up(5 * k.n_m + 1, 4);
@@ -928,7 +930,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
 
     /* launch geometry: shared-memory budget -> warps per CTA, check nodes per warp, frames per group, step schedule */
     if (N >= (1 << 20) || E >= (1 << 24)) { ctx_err(c, "code too large for the packed graph tables (N < 2^20, E < 2^24)"); nbgpu_destroy(c); return NBGPU_EINVAL; }
-    const int budget = getenv("NBGPU_SMEM_KB") ? atoi(getenv("NBGPU_SMEM_KB")) * 1024 : (CTAS_PER_SM > 1 ? (227 * 1024) / CTAS_PER_SM - 1024 : 216 * 1024);
+    const int budget = getenv("NBGPU_SMEM_KB") ? atoi(getenv("NBGPU_SMEM_KB")) * 1024 : (CTAS_PER_SM > 1 ? (228 * 1024) / CTAS_PER_SM - 1024 : 216 * 1024);
     k.F = 1;
     int nw = getenv("NBGPU_WARPS") ? atoi(getenv("NBGPU_WARPS")) : NT_MAX / 32, cpw = getenv("NBGPU_CPW") ? atoi(getenv("NBGPU_CPW")) : 8;
     /* the register budget is what limits residency: keep all NT_MAX/32 warps and shrink the tile before dropping warps */
