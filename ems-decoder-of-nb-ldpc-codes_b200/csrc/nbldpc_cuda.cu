@@ -837,9 +837,10 @@ static void plan_smem(KArgs &k, int nw, int cpw)
         /* syndrome check node: CTA-wide configuration table, then per warp: scratch | lists | keys x2 | payload x2 | gf | hist | M | upd | perm */
         k.off_cfg = off; off += align_up(k.S * k.dc_max, 16);
         int wb2 = 0;
-        k.wb_scr1 = wb2; k.wb_scr3 = wb2; wb2 += align_up(s1, 16);
         k.wb_U = wb2; k.wb_R = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
-        k.sw_key = wb2; wb2 += 2 * 4 * k.Spad;
+        /* the selection scratch of phase 1 is dead once the node's lists are written: it aliases the sort buffers */
+        k.wb_scr1 = wb2; k.wb_scr3 = wb2;
+        k.sw_key = wb2; wb2 += std::max(2 * 4 * k.Spad, align_up(s1, 16));
         k.sw_pay = wb2; wb2 += 2 * 2 * k.Spad;
         k.sw_gf = wb2; wb2 += k.Spad;
         k.sw_hist = wb2; wb2 += 256 * 4;

@@ -90,21 +90,45 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
         __syncwarp();
     }
     /* ---- syndromes, :64-77 ---- */
-    for (int i = lane; i < sm.Spad; i += 32) {
-        uint32_t key = 0xffffffffu, gf = 0, pay = 0xffffu;
-        if (i < sm.S) {
-            float llr = 0.0f;
-            for (int j = 0; j < dc; j++) {
-                const uint32_t list = sm.lists + lds_u32(sm.perm + 4 * j) * sm.lstride;
-                const uint32_t c = lds_u8(sm.cfg + i * dc + j);
-                llr = __fadd_rn(llr, lds_f32(list + 4 * c));
-                gf ^= lds_u8(list + 4 * n_m + c);
+    if (dc == 4) {                                   /* the usual degree: list bases in registers, one table word per configuration */
+        uint32_t lb[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) lb[j] = sm.lists + lds_u32(sm.perm + 4 * j) * sm.lstride;
+        for (int i = lane; i < sm.Spad; i += 32) {
+            uint32_t key = 0xffffffffu, pay = 0xffffu;
+            if (i < sm.S) {
+                const uint32_t cw = lds_u32(sm.cfg + 4 * i);
+                float llr = 0.0f;
+                uint32_t gf = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t c = (cw >> (8 * j)) & 255u;
+                    llr = __fadd_rn(llr, lds_f32(lb[j] + 4 * c));
+                    gf ^= lds_u8(lb[j] + 4 * n_m + c);
+                }
+                key = __float_as_uint(llr); pay = (uint32_t)i;
+                sts_u8(sm.gf + i, gf);
             }
-            key = __float_as_uint(llr); pay = (uint32_t)i;
-            sts_u8(sm.gf + i, gf);
+            sts_u32(sm.key[0] + 4 * i, key);
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[0] + 2 * i), "h"((unsigned short)pay) : "memory");
         }
-        sts_u32(sm.key[0] + 4 * i, key);
-        asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[0] + 2 * i), "h"((unsigned short)pay) : "memory");
+    } else {
+        for (int i = lane; i < sm.Spad; i += 32) {
+            uint32_t key = 0xffffffffu, gf = 0, pay = 0xffffu;
+            if (i < sm.S) {
+                float llr = 0.0f;
+                for (int j = 0; j < dc; j++) {
+                    const uint32_t list = sm.lists + lds_u32(sm.perm + 4 * j) * sm.lstride;
+                    const uint32_t c = lds_u8(sm.cfg + i * dc + j);
+                    llr = __fadd_rn(llr, lds_f32(list + 4 * c));
+                    gf ^= lds_u8(list + 4 * n_m + c);
+                }
+                key = __float_as_uint(llr); pay = (uint32_t)i;
+                sts_u8(sm.gf + i, gf);
+            }
+            sts_u32(sm.key[0] + 4 * i, key);
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[0] + 2 * i), "h"((unsigned short)pay) : "memory");
+        }
     }
     __syncwarp();
     /* ---- stable LSD radix sort, 4 passes of 8 bits over the f32 bit pattern (sorting(), :1315-1334, is a stable insertion
