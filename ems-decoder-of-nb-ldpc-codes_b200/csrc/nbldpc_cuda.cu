@@ -39,6 +39,9 @@
 #define CTAS_PER_SM 2      /* resident CTAs per SM the decode kernel is compiled for (register cap 65536 / (NT_MAX * CTAS_PER_SM)) */
 #endif
 #define NE 2              /* edges interleaved per warp in phases 1 and 3 */
+#ifndef NB_L2_PREFETCH
+#define NB_L2_PREFETCH 1   /* phase 1 pulls the next pair's APP rows and records into L2 while the current pair is selected */
+#endif
 
 #define UNIT_NT 256       /* block size of the small unit-boundary kernels */
 
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                     const int e0 = mt.x, dc = mt.y;
                     float *app_f = app + mt.z * frame_app;
                     const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
-                    if (c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
+                    if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
                     for (int t = 0; t < dc; t += NE) {
                         float v[NE][VPL];
                         RecView r[NE];
@@ -378,7 +381,8 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                             r[e] = load_record(ctov_f, ed, rl);
                         }
                         /* next pair of edges of the tile -> L2 while this pair is processed */
-                        if (t + NE < dc) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0 + t + NE, min(NE, dc - t - NE), rs, lane);
+                        if (!NB_L2_PREFETCH) { }
+                        else if (t + NE < dc) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0 + t + NE, min(NE, dc - t - NE), rs, lane);
                         else if (c + 1 < cnt) {
                             const int4 nx = wm.meta[c + 1];
                             if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
@@ -1061,7 +1065,7 @@ static int upload_common(nbgpu_ctx *c, const float *src, size_t per_frame, int B
     if (!c || !src) { ctx_err(c, "NULL argument"); return NBGPU_EINVAL; }
     if (B < 1 || B > c->max_batch) { ctx_err(c, "B=%d outside 1..max_batch=%d", B, c->max_batch); return NBGPU_EINVAL; }
     CK(c, cudaSetDevice(c->device));
-    int rc = ensure_input(c, per_frame * (size_t)c->max_batch);
+    int rc = ensure_input(c, per_frame * (size_t)B);          /* grows on demand: dense-LLR batches are q/log2(q) times larger */
     if (rc) return rc;
     CK(c, cudaMemcpyAsync(c->d_in, src, per_frame * B * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     c->resident_B = B; c->resident_kind = kind;
@@ -1190,7 +1194,7 @@ static int decode_host(nbgpu_ctx *c, const float *src, size_t per_frame, int kin
         return NBGPU_OK;
     }
     CK(c, cudaSetDevice(c->device));
-    int rc = ensure_input(c, per_frame * (size_t)c->max_batch);
+    int rc = ensure_input(c, per_frame * (size_t)B);
     if (rc) return rc;
     c->resident_B = B; c->resident_kind = kind;
     int lo[5];

@@ -62,6 +62,15 @@ template <int Q, bool CLOSED> __device__ __forceinline__ int gf_rot_out(const GF
     }
 }
 
+/* ---- explicit shared-window accesses (32-bit addresses: no generic-pointer arithmetic in hot loops) ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 /* ---- row I/O: a warp moves one q-float row; lane holds symbols lane*VPL .. lane*VPL+VPL-1 ---- */
 template <int Q> __device__ __forceinline__ void load_row(const float *row, int lane, float (&v)[QTraits<Q>::VPL])
 {
@@ -89,10 +98,9 @@ template <int Q> __device__ __forceinline__ void store_row(float *row, int lane,
 }
 template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, float x)
 {
-    if constexpr (Q == 256) {
-        const float4 q4 = make_float4(x, x, x, x);
-        reinterpret_cast<float4 *>(row)[lane * 2] = q4;
-        reinterpret_cast<float4 *>(row)[lane * 2 + 1] = q4;
+    if constexpr (Q == 256) {                        /* one register, stored as a quad twice: no broadcast moves */
+        const uint32_t a = smem_u32(row) + lane * 32;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+16], {%1, %1, %1, %1};" :: "r"(a), "f"(x) : "memory");
     } else if constexpr (Q == 64) {
         reinterpret_cast<float2 *>(row)[lane] = make_float2(x, x);
     } else {
@@ -211,15 +219,6 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
     warp_lexmin(bv, bg);
     return (bg == 0x7fffffff) ? 0 : bg;
 }
-
-/* ---- explicit shared-window accesses (32-bit addresses: no generic-pointer arithmetic in hot loops) ---- */
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
 /*
  * Truncation of V->C messages (NB_LDPC.c:354-374) for NE edges at once: the n_m smallest of the q
