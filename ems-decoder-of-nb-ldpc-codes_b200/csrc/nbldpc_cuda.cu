@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
     const int F = a.F, N = a.N, n_m = a.n_m, dcm = a.dc_max, rs = a.rec_stride;
     const size_t frame_app = (size_t)N * Q, frame_ctov = (size_t)a.E * rs;
     const RecLane rl(n_m, lane, rs);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     float *app = a.app + blockIdx.x * F * frame_app;
     uint8_t *ctov = a.ctov + blockIdx.x * F * frame_ctov;
     uint8_t *dec = a.dec + (size_t)blockIdx.x * F * N;
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                             const uint32_t ei = wm.ew[c * dcm + te];
                             hv[e] = (ei >> 20) & 0xff;
                             prow[e] = app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q);
-                            load_row<Q>(prow[e], lane, v[e]);
+                            load_row_hint<Q>(prow[e], lane, v[e], pol_stream);
                             r[e] = load_record(ctov_f, ed, rl);
                         }
                         /* next pair of edges of the tile -> L2 while this pair is processed */
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                             expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
 #pragma unroll
                             for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
-                            if (t + e < dc) store_row<Q>(prow[e], lane, v[e]);     /* parked for phase 3 (NB_LDPC.c:448 adds this vector) */
+                            if (t + e < dc) store_row_hint<Q>(prow[e], lane, v[e], pol_keep);     /* parked for phase 3 (NB_LDPC.c:448 adds this vector) */
                         }
                         float llr[NE]; int sym[NE];
                         select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
                             ei[e] = wm.ew[c * dcm + min(t + e, dc - 1)];
-                            load_row<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e]);    /* the Mvc row parked by phase 1 */
+                            load_row_hint<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e], pol_stream);    /* the Mvc row parked by phase 1 */
                         }
 #pragma unroll
                         for (int e = 0; e < NE; e++) {
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                                 expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr3[e]), mcv);    /* :262-281 */
 #pragma unroll
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
-                                store_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v[e]);
+                                store_row_hint<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v[e], pol_stream);
                                 if (ei[e] >> 28) {                                                     /* tools.c:312 fused */
                                     const int d = warp_argmin<Q>(v[e], lane);
                                     if (lane == 0) dec_f[var] = (uint8_t)d;

@@ -96,6 +96,45 @@ template <int Q> __device__ __forceinline__ void store_row(float *row, int lane,
         if (lane < Q) row[lane] = v[0];
     }
 }
+/* ---- the same row moves with an L2 eviction policy (createpolicy): a parked row is wanted again a few microseconds
+ * later (evict_last); APP rows and records are touched once per pass and are streamed (evict_first) ---- */
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4 *p, uint64_t pol)
+{
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_f4_hint(float4 *p, const float4 &v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+template <int Q> __device__ __forceinline__ void load_row_hint(const float *row, int lane, float (&v)[QTraits<Q>::VPL], uint64_t pol)
+{
+    if constexpr (Q == 256) {
+        const float4 a = ldg_f4_hint(reinterpret_cast<const float4 *>(row) + lane * 2, pol);
+        const float4 b = ldg_f4_hint(reinterpret_cast<const float4 *>(row) + lane * 2 + 1, pol);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        load_row<Q>(row, lane, v);
+    }
+}
+template <int Q> __device__ __forceinline__ void store_row_hint(float *row, int lane, const float (&v)[QTraits<Q>::VPL], uint64_t pol)
+{
+    if constexpr (Q == 256) {
+        stg_f4_hint(reinterpret_cast<float4 *>(row) + lane * 2, make_float4(v[0], v[1], v[2], v[3]), pol);
+        stg_f4_hint(reinterpret_cast<float4 *>(row) + lane * 2 + 1, make_float4(v[4], v[5], v[6], v[7]), pol);
+    } else {
+        store_row<Q>(row, lane, v);
+    }
+}
 template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, float x)
 {
     if constexpr (Q == 256) {                        /* one register, stored as a quad twice: no broadcast moves */
