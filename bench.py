@@ -347,7 +347,7 @@ def ours(args, rank, local_rank, world):
         tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl)
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            if tj.get("frames") == B:
+            if tj.get("frames") == B and tj.get("ecn", "bubble") == args.ecn:
                 traffic = tj.get("dram_bytes_per_launch")
         line = {"metric": "decoded info Mbit/s at fixed iterations (%d passes)" % passes, "value": value, "unit": "Mbit/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -191,15 +191,19 @@ __device__ __forceinline__ RecView finish_list(const Lists &ls, uint32_t list, i
     r.sat = __fadd_rn(len > 0 ? last : NB_SENT, offset);             /* :264 (len == 0 cannot occur) */
     return r;
 }
-/* LLR intake for one variable (channel.c:66-76), one warp: lanes < 2*logq first build the per-bit
- * terms (double)((y-s)^2) / (2 sigma^2), then every lane accumulates its symbols bit by bit with the
- * reference's float <- double + double rounding. */
+/* LLR intake for one variable (channel.c:66-76), one warp.  The reference accumulates, for every symbol g and bit b in
+ * ascending order, acc = (float)((double)acc + (double)((y_b - s_b(g))^2) / (2 sigma^2)).  The value after bits 0..k only
+ * depends on the low k+1 bits of the symbol's binary image, so the sums are built as a binary tree over the image bits
+ * (same additions in the same order, each computed once): lane L owns the images whose low five bits are L, the remaining
+ * bits fan out in registers.  t[2b + bit] are the per-bit terms; row is a q-float scratch used to go from image order to
+ * symbol order. */
 template <int Q>
 __device__ __forceinline__ void intake_variable(const float *noisy_n, double den, const uint8_t *img, int lane,
-                                                double *t, float (&v)[QTraits<Q>::VPL])
+                                                double *t, float *row, float (&v)[QTraits<Q>::VPL])
 {
     constexpr int VPL = QTraits<Q>::VPL;
     constexpr int LOGQ = QTraits<Q>::LOGQ;
+    constexpr int LOW = LOGQ < 5 ? LOGQ : 5;
     if (lane < 2 * LOGQ) {
         const float y = noisy_n[lane >> 1];
         const float s = (lane & 1) ? -1.0f : 1.0f;                 /* BPSK(b) = 1 - 2b */
@@ -208,17 +212,27 @@ __device__ __forceinline__ void intake_variable(const float *noisy_n, double den
         t[lane] = __ddiv_rn((double)sq, den);
     }
     __syncwarp();
+    float acc = 0.0f;
 #pragma unroll
-    for (int j = 0; j < VPL; j++) {
-        const int g = lane * VPL + j;
-        float acc = 0.0f;
-        if (Q >= 32 || lane < Q) {
-            const int im = img[g];
+    for (int b = 0; b < LOW; b++) acc = __double2float_rn(__dadd_rn((double)acc, t[2 * b + ((lane >> b) & 1)]));
+    float w[VPL];
+    w[0] = acc;
 #pragma unroll
-            for (int b = 0; b < LOGQ; b++) acc = __double2float_rn(__dadd_rn((double)acc, t[2 * b + ((im >> b) & 1)]));
+    for (int b = LOW; b < LOGQ; b++) {                             /* fan out: w[h] for h < 2^(b-LOW) -> 2^(b-LOW+1) values */
+        const int half = 1 << (b - LOW);
+        const double t0 = t[2 * b], t1 = t[2 * b + 1];
+#pragma unroll
+        for (int h = half - 1; h >= 0; h--) {
+            const float base = w[h];
+            w[h + half] = __double2float_rn(__dadd_rn((double)base, t1));
+            w[h] = __double2float_rn(__dadd_rn((double)base, t0));
         }
-        v[j] = acc;
     }
+#pragma unroll
+    for (int h = 0; h < VPL; h++) if (Q >= 32 || lane < Q) row[lane | (h << 5)] = w[h];     /* image index = lane | h << 5 */
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < VPL; j++) v[j] = (Q >= 32 || lane < Q) ? row[img[lane * VPL + j]] : 0.0f;
     __syncwarp();
 }
 
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
             const int f = w / N, n = w - f * N;
             float v[VPL];
             if (a.input_kind == 0) intake_variable<Q>(a.in + ((size_t)(base + f) * N + n) * a.logq, a.den, gf.img, lane,
-                                                      reinterpret_cast<double *>(wm.scr[0]), v);
+                                                      reinterpret_cast<double *>(wm.scr[0]), reinterpret_cast<float *>(wm.scr[0]) + 32, v);
             else load_row<Q>(a.in + ((size_t)(base + f) * N + n) * Q, lane, v);
             store_row<Q>(app + ((size_t)f * N + n) * Q, lane, v);
         }
@@ -713,11 +727,12 @@ __global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const f
     constexpr int VPL = QTraits<Q>::VPL;
     constexpr int UW = UNIT_NT / 32;
     __shared__ double ts[UW][16];
+    __shared__ float rows[UW][Q];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long total = (long)B * a.N;
     for (long r = (long)blockIdx.x * UW + warp; r < total; r += (long)gridDim.x * UW) {
         float v[VPL];
-        intake_variable<Q>(noisy + r * a.logq, a.den, a.img, lane, ts[warp], v);
+        intake_variable<Q>(noisy + r * a.logq, a.den, a.img, lane, ts[warp], rows[warp], v);
         if (llr) store_row<Q>(llr + r * Q, lane, v);
         if (illr) {
             /* full stable sort = q rounds of the exact scan (channel.c:78-91) */
