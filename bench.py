@@ -252,6 +252,8 @@ def ours(args, rank, local_rank, world):
     import nbldpc
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout, next to the JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
