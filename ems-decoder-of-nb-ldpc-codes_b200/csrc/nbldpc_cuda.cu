@@ -1,7 +1,7 @@
 /*
  * nbldpc_cuda.cu -- CUDA layer + C ABI of the B200 EMS NB-LDPC decoder (sm_100a).
  *
- * One persistent CTA per SM decodes one GROUP of F frames at a time, start to finish (all passes,
+ * Persistent CTAs (two per SM) each decode one GROUP of F frames at a time, start to finish (all passes,
  * early termination included), pulling groups from an atomic work queue.  A decoding pass walks the
  * host-built step schedule (nbldpc_host.c): every step holds check nodes that share no variable, so
  * ONE CTA-wide barrier per step reproduces the reference's sequential layered update
@@ -9,18 +9,20 @@
  * runs them through three warp-private phases (no CTA barrier in between, lists in the warp's own
  * shared memory):
  *
- *   phase 1  warp per edge, NE edges interleaved:  Mvc = APP - CtoV (NB_LDPC.c:334), top-n_m
- *            selection + normalisation (:354-374), rotation by the edge coefficient (bubble_decoder.c:133)
+ *   phase 1  warp per edge, NE edges interleaved:  Mvc = APP - CtoV (NB_LDPC.c:334), parked in the APP row;
+ *            top-n_m selection + normalisation (:354-374), rotation by the edge coefficient (bubble_decoder.c:133)
  *   phase 2  THREAD per ElementaryStep, 4 task slots per check node: forward/backward chains with the
  *            merges folded into the rounds where their inputs are ready (bubble_decoder.c:157-227, 316-593)
- *   phase 3  warp per edge, NE edges interleaved:  Mvc recomputed (same two operands, same result),
- *            saturation + offset + expansion to the dense q-vector (bubble_decoder.c:231-281), CtoV
- *            store, APP = Mcv + Mvc (NB_LDPC.c:415-450), fused Decision (tools.c:312)
+ *   phase 3  warp per edge, NE edges interleaved:  parked Mvc reloaded, saturation + offset + expansion to
+ *            the dense q-vector (bubble_decoder.c:231-281), CtoV store, APP = Mcv + Mvc (NB_LDPC.c:415-450),
+ *            fused Decision (tools.c:312)
+ * With ecn = 1 the tile is processed one check node at a time through the syndrome-based node (nbldpc_synd.cuh).
  *
  * HBM layout per resident frame (slot): APP[N][q] f32 (row = 4q bytes, one coalesced warp access);
  * CtoV as one lossless record per edge {llr[n_m] f32, sat f32, stp i32, sym[n_m] u8} -- a dense CtoV
  * row is "stp explicit (symbol, LLR) pairs + one constant" (bubble_decoder.c:262-270); decisions u8.
- * Every APP row is read twice (L2 hit the second time) and written once per edge visit.
+ * Every APP row is read and written twice per edge visit (APP -> parked Mvc -> APP); the parked copy is short-lived and
+ * is given an evict_last L2 policy, the rest is streamed.  The syndrome-based node stores CtoV as dense rows instead.
  */
 #include "nbldpc_device.cuh"
 #include "nbldpc_synd.cuh"
@@ -77,7 +79,7 @@ struct KArgs {
     int ecn, S, Spad, n_cv;
     const uint8_t *cfg;                 /* [S][dc_max] u8 */
     float *ctov_dense;                  /* [slots][E][q] f32 */
-    int off_cfg, sw_key, sw_pay, sw_gf, sw_hist, sw_M, sw_upd, sw_perm;   /* sw_*: offsets inside a warp's list area */
+    int off_cfg, sw_key, sw_pay, sw_gf, sw_hist, sw_M, sw_perm;   /* sw_*: offsets inside a warp's list area */
 };
 
 /* Lists of a warp's tile in shared memory, by 32-bit shared-window address.  c = check node of the
@@ -250,7 +252,7 @@ __device__ __forceinline__ SyndMem make_synd_mem(unsigned char *smem, const KArg
     sm.lists = wb + a.wb_U;
     sm.key[0] = wb + a.sw_key; sm.key[1] = sm.key[0] + 4 * a.Spad;
     sm.pay[0] = wb + a.sw_pay; sm.pay[1] = sm.pay[0] + 2 * a.Spad;
-    sm.gf = wb + a.sw_gf; sm.hist = wb + a.sw_hist; sm.M = wb + a.sw_M; sm.upd = wb + a.sw_upd; sm.perm = wb + a.sw_perm;
+    sm.gf = wb + a.sw_gf; sm.hist = wb + a.sw_hist; sm.M = wb + a.sw_M; sm.perm = wb + a.sw_perm;
     sm.cfg = smem_u32(smem + a.off_cfg);
     sm.lstride = a.lstride; sm.n_m = a.n_m; sm.dc = a.dc_max; sm.S = a.S; sm.Spad = a.Spad; sm.n_cv = a.n_cv;
     return sm;
@@ -865,7 +867,6 @@ static void plan_smem(KArgs &k, int nw, int cpw)
         k.sw_gf = wb2; wb2 += k.Spad;
         k.sw_hist = wb2; wb2 += 256 * 4;
         k.sw_M = wb2; wb2 += 256 * 4;
-        k.sw_upd = wb2; wb2 += 256;
         k.sw_perm = wb2; wb2 += 80;
         k.wb_bytes = align_up(wb2, 16);
     }

@@ -12,6 +12,8 @@
  *   4. per edge d (presorted position): walk the sorted syndromes whose configuration does not deviate on
  *      d ("decorrelation"), add the edge's best symbol, first hit of a symbol sets its LLR, later hits
  *      go through bayes() in order; saturation at the LLR of decorrelated syndrome n_cv-1+3d, + offset.
+ *      Hits of different symbols never interact, so a fifth stable radix pass groups the sorted list by symbol
+ *      and every lane replays the hits of its own eight symbols -- same order inside a symbol, no conflicts.
  * Symbols are binary images (GF addition == XOR) exactly as in the bubble path.
  */
 #pragma once
@@ -28,7 +30,6 @@ struct SyndMem {
     uint32_t hist;       /* [256] u32 radix histogram; afterwards f32 output LLRs of the current edge,
                             indexed by binary image                                                      */
     uint32_t M;          /* [256] u32 first position of every symbol group in the symbol-grouped order    */
-    uint32_t upd;        /* (unused)                                                                     */
     uint32_t perm;       /* [16] i32: original edge at presorted position i; [16] = sat of the current edge */
     uint32_t cfg;        /* [S][dc] u8 configuration table (shared by the CTA)                          */
     int lstride, n_m, dc, S, Spad, n_cv;
