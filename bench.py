@@ -367,6 +367,22 @@ def ours(args, rank, local_rank, world):
                 "clocks": clocks,
                 "counters": {"frames_per_step": int(counters[0]), "frames_nonzero_syndrome": int(counters[1]), "sum_iterations": int(counters[2]),
                              "slow_path_selects": dec.slow_selects()}}
+        if world == 1 and args.ecn == "bubble" and not args.no_also and n_m in SYND and code.dc_min == code.dc_max and 4 <= code.dc_max <= 8:
+            # the same frames through the reference's other check node (syndrome_ems): a short extra leg, not the headline
+            dec.close()
+            Bs = min(B, args.frames or SYND_FRAMES.get(wl, B))
+            d1, d2, d3, trunc, n_cv = SYND[n_m]
+            ds = nbldpc.Decoder(code, n_m, nb_oper, NB_ITER_MAX, offset, early_stop=False, device=local_rank, max_batch=Bs,
+                                ecn_kind=1, d1=d1, d2=d2, d3=d3, cfg_trunc=trunc, n_cv=n_cv)
+            ds.upload_noisy(noisy[:Bs], sigma)
+            ds.run(); ds.sync()
+            ds.timer_begin()
+            ds.run(); ds.run()
+            sms = ds.timer_end() / 2
+            line["also"] = {"check_node": "syndrome_ems d=(%d,%d,%d), %d configurations max, n_cv=%d" % SYND[n_m], "value": Bs / (sms / 1e3) * code.info_bits / 1e6,
+                            "unit": "Mbit/s", "frames_per_step": Bs, "ms_per_step": sms, "steps": 2, "warmup": 1,
+                            "note": "same workload with NB_LDPC.c:388 instead of :392 as check node; run `bench.py --ecn syndrome` for its full line"}
+            ds.close()
         if world == 1 and not args.no_cpu:
             cores = host_cores()
             rate, kind, sample, wall, nfr = run_reference_cpu(wl, cpu_sample_size(wl, args.ecn), cores, ecn=args.ecn)
@@ -399,6 +415,7 @@ def main():
     ap.add_argument("--frames-per-cta", type=int, default=0)
     ap.add_argument("--cns-per-step", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-also", action="store_true", help="skip the short syndrome_ems leg of the default run")
     ap.add_argument("--count-errors", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

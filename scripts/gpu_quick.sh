@@ -4,7 +4,7 @@
 WL=${1:-AD_64800_R12_GF256}; shift
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --workload $WL "$@" > gpurun_out/bench_$WL.json 2> gpurun_out/bench_$WL.err
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-also --workload $WL "$@" > gpurun_out/bench_$WL.json 2> gpurun_out/bench_$WL.err
 python - <<PY
 import json
 j = json.load(open('gpurun_out/bench_$WL.json'))

@@ -4,7 +4,7 @@
 WL=$1; shift
 mkdir -p gpurun_out
 for E in "$@"; do
-  env $E timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --workload $WL > gpurun_out/sweep.json 2> gpurun_out/sweep.err || tail -3 gpurun_out/sweep.err
+  env $E timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-also --workload $WL > gpurun_out/sweep.json 2> gpurun_out/sweep.err || tail -3 gpurun_out/sweep.err
   python - "$E" <<PY
 import json, sys
 j = json.load(open('gpurun_out/sweep.json'))
