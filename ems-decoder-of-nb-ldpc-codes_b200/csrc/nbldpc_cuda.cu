@@ -245,12 +245,13 @@ __device__ __forceinline__ void load_gf_tables(unsigned char *smem, const KArgs 
     gf.img = tab; gf.inv = tab + 256; gf.rotin = a.rotin; gf.rotout = a.rotout;
 }
 
+__device__ __forceinline__ int std_max_i(int a, int b) { return a > b ? a : b; }
 __device__ __forceinline__ SyndMem make_synd_mem(unsigned char *smem, const KArgs &a, int warp)
 {
     SyndMem sm;
     const uint32_t wb = smem_u32(smem + a.off_wb + warp * a.wb_bytes);
     sm.lists = wb + a.wb_U;
-    sm.key[0] = wb + a.sw_key; sm.key[1] = sm.key[0] + 4 * a.Spad;
+    sm.key[0] = wb + a.sw_key; sm.key[1] = sm.key[0] + std_max_i(4 * a.Spad, 4096);   /* buffer 0 later holds 4 output rows of 256 f32 */
     sm.pay[0] = wb + a.sw_pay; sm.pay[1] = sm.pay[0] + 2 * a.Spad;
     sm.gf = wb + a.sw_gf; sm.hist = wb + a.sw_hist; sm.M = wb + a.sw_M; sm.perm = wb + a.sw_perm;
     sm.cfg = smem_u32(smem + a.off_cfg);
@@ -266,12 +267,12 @@ __device__ __forceinline__ void load_cfg_table(unsigned char *smem, const KArgs 
 /* dense output row of one edge from the syndrome check node: Mcv[s] = M[img(MULGF[s][h])] (syndrome_decoder.c:260-266
  * followed by the scatter NB_LDPC.c:415-421) */
 template <int Q, bool CLOSED>
-__device__ __forceinline__ void synd_dense_row(const SyndMem &sm, const GFTab &gf, int h, int lane, float (&mcv)[QTraits<Q>::VPL])
+__device__ __forceinline__ void synd_dense_row(uint32_t out, const GFTab &gf, int h, int lane, float (&mcv)[QTraits<Q>::VPL])
 {
 #pragma unroll
     for (int j = 0; j < QTraits<Q>::VPL; j++) {
         const int s = lane * QTraits<Q>::VPL + j;
-        mcv[j] = (Q >= 32 || lane < Q) ? lds_f32(sm.hist + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)) : NB_SENT;
+        mcv[j] = (Q >= 32 || lane < Q) ? lds_f32(out + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)) : NB_SENT;
     }
 }
 
@@ -503,14 +504,16 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
                         }
                         __syncwarp();
                         synd_prepare(sm, lane);
+                        synd_sats(sm, lane);
                         for (int d = 0; d < dc; d++) {
-                            synd_edge(sm, d, a.offset, lane);
+                            if ((d & 3) == 0) synd_walk(sm, d, min(4, dc - d), a.offset, lane);
+                            const uint32_t out = sm.key[0] + 1024 * (d & 3);
                             const int t = (int)lds_u32(sm.perm + 4 * d);                   /* un-permute, syndrome_decoder.c:234-253 */
                             const uint32_t ed = (uint32_t)(e0 + t);
-                            const uint32_t ei = a.einfo[ed];
+                            const uint32_t ei = wm.ew[c * dcm + t];
                             const uint32_t var = ei & 0xfffffu;
                             float mcv[VPL], v[VPL], cv[VPL];
-                            synd_dense_row<Q, CLOSED>(sm, gf, (ei >> 20) & 0xff, lane, mcv);
+                            synd_dense_row<Q, CLOSED>(out, gf, (ei >> 20) & 0xff, lane, mcv);
                             load_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v);
                             load_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, cv);
 #pragma unroll
@@ -670,13 +673,15 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_synd_kernel(const KArgs a
         }
         __syncwarp();
         synd_prepare(sm, lane);
+        synd_sats(sm, lane);
         for (int d = 0; d < dc; d++) {
-            synd_edge(sm, d, a.offset, lane);
+            if ((d & 3) == 0) synd_walk(sm, d, min(4, dc - d), a.offset, lane);
+            const uint32_t out = sm.key[0] + 1024 * (d & 3);
             const int t = (int)lds_u32(sm.perm + 4 * d);
             float *dst = cllr + ((size_t)b * dc + t) * Q;
             int *gdst = cgf + ((size_t)b * dc + t) * Q;
             for (int k = lane; k < Q; k += 32) {
-                dst[k] = lds_f32(sm.hist + 4 * gf.img[k]);
+                dst[k] = lds_f32(out + 4 * gf.img[k]);
                 gdst[k] = gf_rot_out<Q, CLOSED>(gf, gf.img[k], a.hval[e0 + t]);
             }
             __syncwarp();
@@ -862,12 +867,12 @@ static void plan_smem(KArgs &k, int nw, int cpw)
         k.wb_U = wb2; k.wb_R = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
         /* the selection scratch of phase 1 is dead once the node's lists are written: it aliases the sort buffers */
         k.wb_scr1 = wb2; k.wb_scr3 = wb2;
-        k.sw_key = wb2; wb2 += std::max(2 * 4 * k.Spad, align_up(s1, 16));
+        k.sw_key = wb2; wb2 += std::max(2 * std::max(4 * k.Spad, 4096), align_up(s1, 16));
         k.sw_pay = wb2; wb2 += 2 * 2 * k.Spad;
         k.sw_gf = wb2; wb2 += k.Spad;
         k.sw_hist = wb2; wb2 += 256 * 4;
         k.sw_M = wb2; wb2 += 256 * 4;
-        k.sw_perm = wb2; wb2 += 80;
+        k.sw_perm = wb2; wb2 += 128;         /* perm[16] i32 | sat[16] f32 */
         k.wb_bytes = align_up(wb2, 16);
     }
     k.off_wb = off; off += nw * k.wb_bytes;

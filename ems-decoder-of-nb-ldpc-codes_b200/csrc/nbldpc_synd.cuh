@@ -193,58 +193,107 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
     }
 }
 
-/* step 4 for presorted position d: on return M'[256] (sm.hist, indexed by binary image of the rotated symbol) holds
- * M_CtoV_LLR[d][.] after saturation (syndrome_decoder.c:93-209).  The reference walks the sorted syndromes and, per symbol,
- * lets the first hit set the LLR and every later hit go through bayes(); hits of different symbols do not interact, so each
- * lane replays the hits of its own eight symbols from the symbol-grouped copy (same order inside a symbol). */
-__device__ __forceinline__ void synd_edge(const SyndMem &sm, int d, float offset, int lane)
+/* Branch-free bayes(): every lane of the walk below evaluates it on every hit, so divergence would cost more than the
+ * few extra instructions (same operations and roundings as synd_bayes). */
+__device__ __forceinline__ float synd_bayes_sel(float m1, float m2)
+{
+    const float mn = fminf(m1, m2), hi = fmaxf(m1, m2);          /* M1 < M2 ? (M1, M2) : (M2, M1); equal values give the same pair */
+    const float dif = __double2float_rn(__dsub_rn((double)hi, (double)mn));
+    const float f = dif < 0.1f ? 0.5f : dif < 0.2f ? 0.75f : dif < 2.0f ? 0.9375f : 1.0f;
+    const float a = __fmul_rn(f, mn);
+    const float b = __double2float_rn(__dmul_rn(0.825, (double)mn));
+    return (dif >= 0.2f && dif < 1.0f) ? b : a;
+}
+
+/* step 4, saturation levels: sat_d = LLR of decorrelated syndrome number n_cv-1+3d in the sorted order (:195), for every
+ * presorted position d; stored as f32 at sm.perm + 64 + 4d.  Must run before synd_walk overwrites the sorted buffer. */
+__device__ __forceinline__ void synd_sats(const SyndMem &sm, int lane)
 {
     const int dc = sm.dc;
     const unsigned lt = (1u << lane) - 1u;
-    const uint32_t x = lds_u8(sm.lists + lds_u32(sm.perm + 4 * d) * sm.lstride + 4 * sm.n_m);   /* M_VtoC_GF[d][0], :103 */
-    /* saturation level: LLR of decorrelated syndrome number n_cv-1+3d in the sorted order, :195 */
-    const int target = sm.n_cv - 1 + 3 * d;
-    float sat = 0.0f;
-    int cnt = 0;
-    for (int i = lane; i < sm.Spad; i += 32) {
-        unsigned short p;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[0] + 2 * i));
-        const bool keep = (int)p < sm.S && lds_u8(sm.cfg + (int)p * dc + d) == 0;             /* :96-98 */
-        const unsigned bal = __ballot_sync(NB_FULL, keep);
-        const int n = __popc(bal);
-        if (cnt + n > target) {
-            const bool mine = keep && cnt + __popc(bal & lt) == target;
-            const unsigned who = __ballot_sync(NB_FULL, mine);
-            sat = __shfl_sync(NB_FULL, __uint_as_float(lds_u32(sm.key[0] + 4 * i)), __ffs(who) - 1);
-            break;
+    for (int d = 0; d < dc; d++) {
+        const int target = sm.n_cv - 1 + 3 * d;
+        float sat = 0.0f;
+        int cnt = 0;
+        for (int i = lane; i < sm.Spad; i += 32) {
+            unsigned short p;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[0] + 2 * i));
+            const bool keep = (int)p < sm.S && lds_u8(sm.cfg + (int)p * dc + d) == 0;         /* :96-98 */
+            const unsigned bal = __ballot_sync(NB_FULL, keep);
+            const int n = __popc(bal);
+            if (cnt + n > target) {
+                const bool mine = keep && cnt + __popc(bal & lt) == target;
+                const unsigned who = __ballot_sync(NB_FULL, mine);
+                sat = __shfl_sync(NB_FULL, __uint_as_float(lds_u32(sm.key[0] + 4 * i)), __ffs(who) - 1);
+                break;
+            }
+            cnt += n;
         }
-        cnt += n;
+        if (lane == 0) sts_f32(sm.perm + 64 + 4 * d, sat);
     }
-    const float hi = __fadd_rn(sat, offset);
-    /* per symbol: first hit sets, later hits through bayes, :128-164; then saturation, :198-209.
-     * Lane L owns the output symbols 8L..8L+7; they receive the syndromes of the groups (8L+b)^x, i.e. of the eight
-     * CONSECUTIVE groups 8(L^(x>>3)) .. +7: one contiguous range of the symbol-grouped order, walked once. */
-    const uint32_t out = sm.hist + 4 * (lane * 8);
+    __syncwarp();
+}
+
+/* step 4 for the presorted positions d0 .. d0+nd-1 (nd <= 4) in ONE walk: on return out_k[256] = sm.key[0] + 1024 k
+ * (f32, indexed by the binary image of the rotated symbol) holds M_CtoV_LLR[d0+k][.] after saturation
+ * (syndrome_decoder.c:93-209).  The reference walks the sorted syndromes and, per symbol, lets the first hit set the LLR
+ * and every later hit go through bayes(); hits of different symbols do not interact, so lane L replays the syndromes of
+ * the symbol groups 8L..8L+7 (one contiguous range of the symbol-grouped order, ascending inside a group) for all nd
+ * edges at once and scatters the results to the symbols (group ^ best symbol of the edge). */
+__device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, float offset, int lane)
+{
+    const int dc = sm.dc;
+    uint32_t x[4]; float sat[4], hi[4], m[4];
 #pragma unroll
-    for (int b = 0; b < 8; b++) sts_f32(out + 4 * b, hi);               /* symbols without a hit: 1500 > sat -> sat + offset */
-    const uint32_t g0 = ((uint32_t)lane ^ (x >> 3)) * 8u;
+    for (int k = 0; k < 4; k++) {
+        const int d = d0 + (k < nd ? k : 0);
+        x[k] = lds_u8(sm.lists + lds_u32(sm.perm + 4 * d) * sm.lstride + 4 * sm.n_m);        /* M_VtoC_GF[d][0], :103 */
+        sat[k] = lds_f32(sm.perm + 64 + 4 * d);
+        hi[k] = __fadd_rn(sat[k], offset);
+        m[k] = 0.0f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; k++)                                  /* symbols without a hit: 1500 > sat -> sat + offset, :131, :198-209 */
+        if (k < nd) {
+            const uint32_t a = sm.key[0] + 1024 * k + lane * 32;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+16], {%1, %1, %1, %1};" :: "r"(a), "f"(hi[k]) : "memory");
+        }
+    __syncwarp();
+    const uint32_t g0 = (uint32_t)lane * 8u;
     const int lo = (int)lds_u32(sm.M + 4 * g0);
     const int hi_i = g0 + 8u >= 256u ? sm.Spad : (int)lds_u32(sm.M + 4 * (g0 + 8u));
-    int cur = -1;
-    float m = 0.0f;
-    for (int i = lo; i < hi_i; i++) {
-        unsigned short p;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[1] + 2 * i));
-        if ((int)p >= sm.S || lds_u8(sm.cfg + (int)p * dc + d) != 0) continue;
-        const int sy = (int)((lds_u8(sm.gf + p) ^ x) & 7u);
-        const float llr = __uint_as_float(lds_u32(sm.key[1] + 4 * i));
-        if (sy != cur) {
-            if (cur >= 0) sts_f32(out + 4 * cur, m > sat ? hi : m);
-            cur = sy; m = llr;
-        } else {
-            m = synd_bayes(llr, m);
+    uint32_t cur = 0xffffffffu, have = 0u;
+    for (int i = lo; i <= hi_i; i++) {                           /* one extra trip flushes the last group */
+        uint32_t p = 0xffffu, g = 0xfffffffeu, cw = 0xffffffffu;
+        float llr = 0.0f;
+        if (i < hi_i) {
+            unsigned short ps;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ps) : "r"(sm.pay[1] + 2 * i));
+            p = ps;
+            if ((int)p >= sm.S) continue;                        /* padding (tail of group 255) */
+            g = lds_u8(sm.gf + p);
+            llr = __uint_as_float(lds_u32(sm.key[1] + 4 * i));
+            if (dc == 4) cw = lds_u32(sm.cfg + 4 * p);
+            else {
+                cw = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; k++) cw |= (k < nd ? lds_u8(sm.cfg + p * dc + d0 + k) : 1u) << (8 * k);
+            }
+        }
+        if (g != cur) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((have >> k) & 1u) sts_f32(sm.key[0] + 1024 * k + 4 * ((cur ^ x[k]) & 255u), m[k] > sat[k] ? hi[k] : m[k]);
+            cur = g; have = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < nd && ((cw >> (8 * k)) & 255u) == 0u) {      /* decorrelation, :96-98 */
+                m[k] = ((have >> k) & 1u) ? synd_bayes_sel(llr, m[k]) : llr;
+                have |= 1u << k;
+            }
         }
     }
-    if (cur >= 0) sts_f32(out + 4 * cur, m > sat ? hi : m);
     __syncwarp();
 }
