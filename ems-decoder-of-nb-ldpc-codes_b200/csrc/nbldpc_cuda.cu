@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs
         }
         if constexpr (ECN == 0) {
             for (int i = tid; i < nf * a.E; i += nthr)       /* CtoV = 0: stp 0, constant 0.0f */
-                *reinterpret_cast<int2 *>(ctov + (size_t)i * rs + 4 * n_m) = make_int2(0, 0);
+                *reinterpret_cast<int2 *>(ctov + (size_t)i * rs + rl.tail) = make_int2(0, 0);
         } else {
             float4 *z = reinterpret_cast<float4 *>(ctov_d);  /* CtoV = 0, NB_LDPC.c:273-279 */
             for (size_t i = tid; i < (size_t)nf * frame_dense / 4; i += nthr) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -915,7 +915,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     k.N = N; k.M = M; k.E = E; k.q = q; k.logq = code->logq; k.dc_max = code->dc_max; k.dc_min = code->dc_min;
     k.n_m = p->n_m; k.nb_oper = p->nb_oper; k.passes = p->nb_iter_max - 1; k.early_stop = p->early_stop;
     k.nb_iter_max = p->nb_iter_max; k.offset = p->offset;
-    k.rec_stride = align_up(5 * p->n_m + 8, 16);
+    k.rec_stride = align_up(((4 * p->n_m + 7) & ~7) + 8 + p->n_m, 16);     /* llr[n_m] f32 | pad to 8 | sat f32, stp i32 | sym[n_m] u8 */
 
     /* tables */
     std::vector<uint8_t> hval(E), last(E, 0), rotin((size_t)q * q), rotout((size_t)q * q), img(q), inv(q);
@@ -1285,9 +1285,10 @@ extern "C" int nbgpu_get_state(nbgpu_ctx *c, int frame, float *APP, float *CtoV)
         for (int e = 0; e < E; e++) {
             const uint8_t *r = rec.data() + (size_t)e * rs;
             float sat; int stp;
-            memcpy(&sat, r + 4 * n_m, 4); memcpy(&stp, r + 4 * n_m + 4, 4);
+            const int tail = (4 * n_m + 7) & ~7;
+            memcpy(&sat, r + tail, 4); memcpy(&stp, r + tail + 4, 4);
             for (int g = 0; g < q; g++) CtoV[(size_t)e * q + g] = sat;
-            for (int kk = 0; kk < stp; kk++) { float l; memcpy(&l, r + 4 * kk, 4); CtoV[(size_t)e * q + r[4 * n_m + 8 + kk]] = l; }
+            for (int kk = 0; kk < stp; kk++) { float l; memcpy(&l, r + 4 * kk, 4); CtoV[(size_t)e * q + r[tail + 8 + kk]] = l; }
         }
     }
     return NBGPU_OK;

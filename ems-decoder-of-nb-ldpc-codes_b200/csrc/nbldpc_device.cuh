@@ -147,7 +147,7 @@ template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, 
     }
 }
 
-/* ---- stored C->V message of one edge ("record"): llr[n_m] f32 | sat f32 | stp i32 | sym[n_m] u8 ----
+/* ---- stored C->V message of one edge ("record"): llr[n_m] f32 | pad to 8 | sat f32 | stp i32 | sym[n_m] u8 ----
  * A dense CtoV row is "stp explicit (symbol, LLR) pairs + the constant sat everywhere else"
  * (bubble_decoder.c:262-270), so the record is lossless. */
 struct RecView {
@@ -160,7 +160,8 @@ struct RecLane {
     __device__ __forceinline__ RecLane(int n_m, int lane, int rec_stride)
     {
         const int k = lane < n_m ? lane : 0;
-        llr = 4 * k; sym = 4 * n_m + 8 + k; tail = 4 * n_m; stride = (uint32_t)rec_stride;
+        tail = (4 * n_m + 7) & ~7;              /* {sat, stp} is accessed as one 8-byte word: keep it aligned for odd n_m */
+        llr = 4 * k; sym = tail + 8 + k; stride = (uint32_t)rec_stride;
     }
 };
 __device__ __forceinline__ RecView load_record(const uint8_t *ctov_f, uint32_t ed, const RecLane &rl)

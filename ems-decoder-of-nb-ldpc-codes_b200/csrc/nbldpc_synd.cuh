@@ -254,10 +254,11 @@ __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, flo
     }
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 4; k++)                                  /* symbols without a hit: 1500 > sat -> sat + offset, :131, :198-209 */
+    for (int k = 0; k < 4; k++)                                  /* symbols without a hit keep the initial 1500.0 (:131), which the saturation (:198-209) turns into sat + offset unless sat >= 1500 */
         if (k < nd) {
             const uint32_t a = sm.key[0] + 1024 * k + lane * 32;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+16], {%1, %1, %1, %1};" :: "r"(a), "f"(hi[k]) : "memory");
+            const float unset = 1500.0f > sat[k] ? hi[k] : 1500.0f;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+16], {%1, %1, %1, %1};" :: "r"(a), "f"(unset) : "memory");
         }
     __syncwarp();
     const uint32_t g0 = (uint32_t)lane * 8u;
