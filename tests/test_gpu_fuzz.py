@@ -91,3 +91,43 @@ def test_random_configuration_equals_oracle(seed, tmp_path):
             app, ctov = d.get_state(0)
             assert app.tobytes() == r["app"].tobytes() and ctov.tobytes() == r["ctov"].tobytes(), seed
     o.close(); d.close()
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_adversarial_llr_inputs_equal_oracle(seed, tmp_path):
+    """Dense-LLR intake with values the channel never produces: small integers (exact ties everywhere -> lowest-symbol /
+    lowest-bubble rules), negative values, entries at or above the 1e5 sentinel, one-hot rows."""
+    rng = np.random.default_rng(5000 + seed)
+    q = int(rng.choice([16, 64, 256]))
+    dc = int(rng.choice([3, 4, 4, 6]))
+    dcs = [dc] * int(rng.integers(3, 8))
+    N = max(dc + 2, len(dcs) + 2, sum(dcs) // 2)
+    a = _random_code(rng, q, N, dcs)
+    path = str(tmp_path / "code.alist")
+    write_alist_ubs(path, a)
+    code = nbldpc.Code(path)
+    o = ol.Oracle(path, code.dialect)
+    n_m = int(rng.integers(5, min(q, 32) + 1))
+    nb_oper = int(rng.integers(4, 40))
+    frames = 12
+    kind = seed % 4
+    if kind == 0:
+        llr = rng.integers(0, 6, (frames, N, q)).astype(np.float32)                       # ties everywhere
+    elif kind == 1:
+        llr = (rng.integers(-8, 24, (frames, N, q)) * 0.5).astype(np.float32)             # negative values too
+    elif kind == 2:
+        llr = (rng.random((frames, N, q)) * 30).astype(np.float32)
+        llr[rng.random(llr.shape) < 0.9] = 1e5                                            # fewer than n_m selectable symbols
+        llr[rng.random(llr.shape) < 0.05] = 2.5e5
+    else:
+        llr = np.full((frames, N, q), 40.0, np.float32)                                   # one-hot rows + a few flips
+        np.put_along_axis(llr, rng.integers(0, q, (frames, N, 1)), 0.0, axis=2)
+    d = nbldpc.Decoder(code, n_m, nb_oper, 5, 0.3, max_batch=frames)
+    dec, synd, it = d.decode_llr(llr)
+    for f in range(frames):
+        r = o.decode_frame(llr[f], n_m, nb_oper, 5, 0.3, want_state=(f < 2))
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"] and it[f] == r["iters"], (seed, f)
+        if f < 2:
+            app, ctov = d.get_state(f)
+            assert np.array_equal(app, r["app"], equal_nan=True) and np.array_equal(ctov, r["ctov"], equal_nan=True), (seed, f)
+    o.close(); d.close()
