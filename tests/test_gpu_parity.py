@@ -414,6 +414,28 @@ def test_full_size_round_trip_and_invariances(rel, n_m, ebn_hi):
     d.close()
 
 
+def test_full_size_multi_wave_batch_spot_checked_against_oracle():
+    """BASELINE config 5 at the operating point of the bench (Eb/N0 2.0 dB, some frames never converge): a batch larger than
+    the persistent grid (several frames per CTA, chunked end-to-end path), six frames spot-checked against the oracle"""
+    rel, n_m = "matrices/AD_64800_R12_GF256", 20
+    code = nbldpc.Code(matrix_path(rel))
+    d = nbldpc.Decoder(code, n_m, 25, 10, 0.3, max_batch=1400)
+    geo = d.geometry()
+    B = min(1400, 4 * geo["grid"] * geo["frames_per_cta"] + 13)
+    fr, sigma = product_frames(code, 6, 2.0)
+    rng = np.random.default_rng(7)
+    pick = rng.integers(0, 6, B)
+    noisy = np.stack([f["noisy"] for f in fr])[pick]
+    noisy = noisy + (rng.standard_normal(noisy.shape) * 0.02).astype(np.float32)       # every frame differs
+    dec, synd, it = d.decode_noisy(noisy, sigma)
+    assert len(set(it.tolist())) > 1, "the batch should mix converging and non-converging frames"
+    o = ol.Oracle(matrix_path(rel), code.dialect)
+    for f in [0, 1, B // 3, B // 2, B - 2, B - 1]:
+        r = o.decode_frame(o.channel_llr(noisy[f], sigma), n_m, 25, 10, 0.3)
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"] and it[f] == r["iters"], f
+    o.close(); d.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # Monte-Carlo statistics: the C driver (csrc/nbldpc_mc.c) and the sharded loop (multigpu.py) against the stock binary
 # ---------------------------------------------------------------------------------------------------
