@@ -333,6 +333,20 @@ def test_chunked_end_to_end_path_equals_single_launch():
     o.close(); d.close()
 
 
+def test_contexts_with_different_geometries_coexist():
+    """two decoders of the same kernel (GF(64), closed form) but different shared-memory plans, used alternately"""
+    c1 = nbldpc.Code(matrix_path("matrices/N96_K48_GF64")); c2 = nbldpc.Code(matrix_path("matrices/Mat24_N480_M240"))
+    d1 = nbldpc.Decoder(c1, 20, 25, 10, 0.3, max_batch=64)
+    d2 = nbldpc.Decoder(c2, 8, 25, 10, 0.3, max_batch=8, cns_per_step=12)
+    assert d1.geometry()["smem_bytes"] != d2.geometry()["smem_bytes"]
+    f1, s1 = product_frames(c1, 64, 2.5); f2, s2 = product_frames(c2, 8, 2.0)
+    n1 = np.stack([f["noisy"] for f in f1]); n2 = np.stack([f["noisy"] for f in f2])
+    a = d1.decode_noisy(n1, s1); b = d2.decode_noisy(n2, s2); a2 = d1.decode_noisy(n1, s1); b2 = d2.decode_noisy(n2, s2)
+    for x, y in zip(a + b, a2 + b2):
+        assert (x == y).all()
+    d1.close(); d2.close()
+
+
 def test_batch_shapes_and_errors():
     code = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
     fr, sigma = product_frames(code, 37, 2.5)
