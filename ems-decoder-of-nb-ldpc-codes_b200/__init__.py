@@ -99,11 +99,17 @@ def lib():
         "nbgpu_geometry": (C.c_int, [vp, _ip]),
         "nbgpu_slow_selects": (C.c_long, [vp]),
         "nbgpu_get_state": (C.c_int, [vp, C.c_int, _fp, _fp]),
+        "nbgpu_source_frames": (C.c_int, [vp, vp, C.POINTER(Rng), C.c_uint64, C.c_int, C.c_float]),
+        "nbgpu_source_download": (C.c_int, [vp, _ip, _fp]),
+        "nbgpu_source_results": (C.c_int, [vp, _ip, _ip, _ip]),
+        "nbgpu_source_fixups": (C.c_long, [vp]),
+        "nbgpu_source_set_margin": (C.c_int, [vp, C.c_double]),
         "nbgpu_check_node": (C.c_int, [vp, C.c_int, _fp, _ip, _fp, _ip, C.c_int]),
         "nbgpu_elementary_step": (C.c_int, [vp, _fp, _fp, _ip, _ip, _fp, _ip, C.c_int]),
         "nbgpu_select_nm": (C.c_int, [vp, _fp, _fp, _ip, C.c_int]),
         "nbgpu_decision_syndrome": (C.c_int, [vp, _fp, _ip, _ip, C.c_int]),
         "nbgpu_accumulate_stats": (C.c_int, [vp, _ip, _ip, _ip, _ip, C.c_int, _lp]),
+        "nbgpu_accumulate_results": (C.c_int, [_ip, _ip, _ip, C.c_int, _lp]),
         "nbgpu_config_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
         "nbgpu_version": (C.c_char_p, []),
         "nbgpu_device_count": (C.c_int, []),
@@ -277,6 +283,34 @@ class Decoder:
         d, s, it = out if out is not None else self._out(self.B)
         _check(lib().nbgpu_download(self.h, _i(d), _i(s), _i(it)), self.h)
         return d, s, it
+
+    def source_frames(self, frame0, B, ebn, origin=None):
+        """nbgpu_source_frames: frames [frame0, frame0+B) of the reference's stream generated on the device and left resident
+        (origin: drand48 state before frame 0 as an int, default = the reference's unseeded stream)."""
+        r = Rng()
+        lib().nbgpu_rng_reference_default(C.byref(r))
+        if origin is not None:
+            r.x = origin
+        _check(lib().nbgpu_source_frames(self.h, self.code.h, C.byref(r), frame0, B, C.c_float(ebn)), self.h)
+        self.B = B
+
+    def source_download(self, want_noisy=True):
+        cw = np.zeros((self.B, self.code.N), np.int32)
+        noisy = np.zeros((self.B, self.code.N, self.code.logq), np.float32) if want_noisy else None
+        _check(lib().nbgpu_source_download(self.h, _i(cw), _f(noisy)), self.h)
+        return cw, noisy
+
+    def source_results(self):
+        """(bit_errors[B], synd[B], iters[B]) of the generated batch after run()"""
+        e, s, it = (np.zeros(self.B, np.int32) for _ in range(3))
+        _check(lib().nbgpu_source_results(self.h, _i(e), _i(s), _i(it)), self.h)
+        return e, s, it
+
+    def source_fixups(self):
+        return int(lib().nbgpu_source_fixups(self.h))
+
+    def source_set_margin(self, margin):
+        _check(lib().nbgpu_source_set_margin(self.h, C.c_double(margin)), self.h)
 
     def last_kernel_ms(self):
         ms = C.c_float(0)

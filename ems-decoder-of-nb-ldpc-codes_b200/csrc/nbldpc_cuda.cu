@@ -26,6 +26,7 @@
  */
 #include "nbldpc_device.cuh"
 #include "nbldpc_synd.cuh"
+#include "nbldpc_source.cuh"
 #include "nbldpc_internal.h"
 #include <cstdarg>
 #include <cstdio>
@@ -799,6 +800,17 @@ struct nbgpu_ctx {
     int *d_decide, *d_synd, *d_iters, *d_frame_slot, *d_slot_frame;
     unsigned *d_queue, *d_slow;
     int resident_B, resident_kind;
+    /* device frame source (nbldpc_source.cuh), set up by the first nbgpu_source_frames */
+    struct {
+        int ready, nlevels, B;
+        int *d_level_ptr, *d_row_order, *d_ut_ptr, *d_ut_col, *d_perm, *d_bit_errors;
+        uint8_t *d_ut_val, *d_piv, *d_mulimg, *d_divimg, *d_cw;
+        unsigned *d_flag_count, *d_flags, *d_patch_idx;
+        float *d_patch_val;
+        uint64_t D;
+        double margin;
+        long fixups;
+    } src;
     long launches;
     float last_ms;
     char err[512];
@@ -1063,6 +1075,10 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
                      c->d_rotout, c->d_img, c->d_inv, c->d_app, c->d_ctov, c->d_dec, c->d_in, c->d_decide, c->d_synd,
                      c->d_iters, c->d_frame_slot, c->d_slot_frame, c->d_queue };
     for (void *b : bufs) if (b) cudaFree(b);
+    void *sbufs[] = { c->src.d_level_ptr, c->src.d_row_order, c->src.d_ut_ptr, c->src.d_ut_col, c->src.d_perm, c->src.d_bit_errors, c->src.d_ut_val,
+                      c->src.d_piv, c->src.d_mulimg, c->src.d_divimg, c->src.d_cw, c->src.d_flag_count, c->src.d_flags, c->src.d_patch_idx,
+                      c->src.d_patch_val };
+    for (void *b : sbufs) if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -1265,6 +1281,169 @@ extern "C" int nbgpu_decode_llr(nbgpu_ctx *c, const float *llr, int B, int *deci
 {
     if (!c) return NBGPU_EINVAL;
     return decode_host(c, llr, (size_t)c->N * c->q, 1, B, decide, synd, iters);
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame source on the device (kernels in nbldpc_source.cuh)
+ * ---------------------------------------------------------------------------------------------- */
+#define SRC_FLAG_CAP (1u << 20)
+
+static int source_setup(nbgpu_ctx *c, nbgpu_code *code)
+{
+    if (code->N != c->N || code->M != c->M || code->q != c->q) { ctx_err(c, "nbgpu_source_frames: the code is not the one the decoder was created for"); return NBGPU_EINVAL; }
+    if (c->N > 48 * 1024) { ctx_err(c, "frame source: N=%d symbols do not fit the encoder's shared memory", c->N); return NBGPU_EINVAL; }
+    int rc = nbgpu_code_prepare_encoder(code);
+    if (rc) { ctx_err(c, "%s", nbgpu_get_global_error()); return rc; }
+    const int N = c->N, M = c->M, q = c->q;
+    /* level of a row = 1 + the deepest parity symbol it reads: rows of one level are independent (tools.c:244 runs m = M-1..0) */
+    std::vector<int> level(M, 0), order(M), lptr;
+    int depth = 0;
+    for (int m = M - 1; m >= 0; m--) {
+        int l = 0;
+        for (int k = code->ut_ptr[m]; k < code->ut_ptr[m + 1]; k++) { const int n = code->ut_col[k]; if (n < M) l = std::max(l, level[n] + 1); }
+        level[m] = l; depth = std::max(depth, l + 1);
+    }
+    lptr.assign(depth + 1, 0);
+    for (int m = 0; m < M; m++) lptr[level[m] + 1]++;
+    for (int l = 0; l < depth; l++) lptr[l + 1] += lptr[l];
+    { std::vector<int> pos(lptr.begin(), lptr.end() - 1); for (int m = M - 1; m >= 0; m--) order[pos[level[m]]++] = m; }
+    const int nnz = code->ut_ptr[M];
+    std::vector<int> utp(code->ut_ptr, code->ut_ptr + M + 1), utc(code->ut_col, code->ut_col + nnz), perm(code->perm, code->perm + N);
+    std::vector<uint8_t> utv(nnz + 1), piv(M), mulimg((size_t)q * q), divimg((size_t)q * q);
+    for (int k = 0; k < nnz; k++) utv[k] = (uint8_t)code->ut_val[k];
+    for (int m = 0; m < M; m++) piv[m] = (uint8_t)code->piv_col[m];
+    for (int h = 0; h < q; h++)
+        for (int x = 0; x < q; x++) {                       /* x = binary image of the operand symbol */
+            const int sx = code->inv[x];
+            mulimg[(size_t)h * q + x] = (uint8_t)code->img[code->mulgf[h * q + sx]];
+            divimg[(size_t)h * q + x] = h ? (uint8_t)code->img[code->divgf[sx * q + h]] : 0;
+        }
+    if ((rc = upload(c, &c->src.d_level_ptr, lptr)) || (rc = upload(c, &c->src.d_row_order, order)) || (rc = upload(c, &c->src.d_ut_ptr, utp)) ||
+        (rc = upload(c, &c->src.d_ut_col, utc)) || (rc = upload(c, &c->src.d_perm, perm)) || (rc = upload(c, &c->src.d_ut_val, utv)) ||
+        (rc = upload(c, &c->src.d_piv, piv)) || (rc = upload(c, &c->src.d_mulimg, mulimg)) || (rc = upload(c, &c->src.d_divimg, divimg))) return rc;
+    CK(c, cudaMalloc((void **)&c->src.d_cw, (size_t)c->max_batch * N));
+    CK(c, cudaMalloc((void **)&c->src.d_bit_errors, (size_t)c->max_batch * sizeof(int)));
+    CK(c, cudaMalloc((void **)&c->src.d_flag_count, sizeof(unsigned)));
+    CK(c, cudaMalloc((void **)&c->src.d_flags, SRC_FLAG_CAP * sizeof(unsigned)));
+    CK(c, cudaMalloc((void **)&c->src.d_patch_idx, SRC_FLAG_CAP * sizeof(unsigned)));
+    CK(c, cudaMalloc((void **)&c->src.d_patch_val, SRC_FLAG_CAP * sizeof(float)));
+    uint64_t mul[48], add[48], m_ = SRC_A, a_ = SRC_C;
+    for (int j = 0; j < 48; j++) { mul[j] = m_; add[j] = a_; a_ = ((m_ + 1) * a_) & SRC_MASK; m_ = (m_ * m_) & SRC_MASK; }
+    CK(c, cudaMemcpyToSymbol(c_src_mul, mul, sizeof mul));
+    CK(c, cudaMemcpyToSymbol(c_src_add, add, sizeof add));
+    c->src.nlevels = depth;
+    c->src.D = (uint64_t)(code->K + 2 * N) * c->logq;
+    if (c->src.margin == 0.0) c->src.margin = 0x1p-46;
+    c->src.ready = 1;
+    return NBGPU_OK;
+}
+
+static SrcArgs source_args(nbgpu_ctx *c, const nbgpu_code *code, int B)
+{
+    SrcArgs a;
+    memset(&a, 0, sizeof a);
+    a.N = c->N; a.M = c->M; a.K = c->N - c->M; a.q = c->q; a.logq = c->logq; a.B = B; a.D = c->src.D; a.nlevels = c->src.nlevels;
+    a.level_ptr = c->src.d_level_ptr; a.row_order = c->src.d_row_order; a.ut_ptr = c->src.d_ut_ptr; a.ut_col = c->src.d_ut_col;
+    a.ut_val = c->src.d_ut_val; a.piv = c->src.d_piv; a.perm = c->src.d_perm; a.mulimg = c->src.d_mulimg; a.divimg = c->src.d_divimg;
+    a.img = c->d_img; a.cw = c->src.d_cw; a.noisy = c->d_in; a.margin = c->src.margin;
+    a.flag_count = c->src.d_flag_count; a.flags = c->src.d_flags; a.flag_cap = SRC_FLAG_CAP;
+    a.decide = c->d_decide; a.bit_errors = c->src.d_bit_errors;
+    (void)code;
+    return a;
+}
+
+extern "C" int nbgpu_source_set_margin(nbgpu_ctx *c, double margin)
+{
+    if (!c || !(margin > 0.0) || margin > 0x1p-20) { ctx_err(c, "nbgpu_source_set_margin: margin must be in (0, 2^-20]"); return NBGPU_EINVAL; }
+    c->src.margin = margin;
+    return NBGPU_OK;
+}
+
+extern "C" int nbgpu_source_frames(nbgpu_ctx *c, nbgpu_code *code, const nbgpu_rng *origin, uint64_t frame0, int B, float EbN)
+{
+    if (!c || !code || !origin) { ctx_err(c, "NULL argument"); return NBGPU_EINVAL; }
+    if (B < 1 || B > c->max_batch) { ctx_err(c, "B=%d outside 1..max_batch=%d", B, c->max_batch); return NBGPU_EINVAL; }
+    if ((double)B * c->N * c->logq >= 2147483648.0) { ctx_err(c, "frame source: B*N*log2(q) must stay below 2^31"); return NBGPU_EINVAL; }
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    if (!c->src.ready && (rc = source_setup(c, code))) return rc;
+    if ((rc = ensure_input(c, (size_t)c->N * c->logq * B))) return rc;
+    const float sigma = nbgpu_sigma(code, EbN);
+    nbgpu_rng r = *origin;
+    nbgpu_rng_skip(&r, frame0 * c->src.D);
+    SrcArgs a = source_args(c, code, B);
+    a.x0 = r.x; a.sigma = sigma;
+    CK(c, cudaMemsetAsync(c->src.d_flag_count, 0, sizeof(unsigned), c->stream));
+    source_encode_kernel<<<B, 256, c->N, c->stream>>>(a);
+    const long long threads = (long long)B * c->N;
+    source_noise_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(a);
+    CK(c, cudaGetLastError());
+    c->launches += 2;
+    unsigned nflag = 0;
+    CK(c, cudaMemcpyAsync(&nflag, c->src.d_flag_count, sizeof nflag, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (nflag > SRC_FLAG_CAP) { ctx_err(c, "frame source: %u samples flagged for host recomputation (capacity %u); margin too wide", nflag, SRC_FLAG_CAP); return NBGPU_EINVAL; }
+    c->src.fixups = nflag;
+    if (nflag) {
+        /* samples whose f32 rounding could depend on the last bits of log/cos: recompute with the host's libm (channel.c:59) */
+        std::vector<unsigned> idx(nflag);
+        std::vector<float> val(nflag);
+        CK(c, cudaMemcpy(idx.data(), c->src.d_flags, nflag * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        const uint64_t per = (uint64_t)c->N * c->logq, koff = (uint64_t)(c->N - c->M) * c->logq;
+        for (unsigned i = 0; i < nflag; i++) {
+            const uint64_t id = idx[i] & 0x7fffffffu, f = id / per, s = id % per;
+            nbgpu_rng g; g.x = a.x0;
+            nbgpu_rng_skip(&g, f * c->src.D + koff + 2 * s);
+            const float u = (float)nbgpu_rng_drand48(&g), v = (float)nbgpu_rng_drand48(&g);
+            val[i] = nbgpu_noise_sample(sigma, u, v, (int)(idx[i] >> 31));
+        }
+        CK(c, cudaMemcpyAsync(c->src.d_patch_idx, idx.data(), nflag * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(c->src.d_patch_val, val.data(), nflag * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        source_patch_kernel<<<(nflag + 255) / 256, 256, 0, c->stream>>>(c->d_in, c->src.d_patch_idx, c->src.d_patch_val, (int)nflag);
+        CK(c, cudaGetLastError());
+        CK(c, cudaStreamSynchronize(c->stream));                 /* idx/val are stack-scoped */
+        c->launches += 1;
+    }
+    c->k.den = 2.0 * (double)(float)(sigma * sigma);            /* 2.0*SQR(sigma), channel.c:73 */
+    c->resident_B = B; c->resident_kind = 0; c->src.B = B;
+    return NBGPU_OK;
+}
+
+extern "C" long nbgpu_source_fixups(const nbgpu_ctx *c) { return c ? c->src.fixups : 0; }
+
+extern "C" int nbgpu_source_download(nbgpu_ctx *c, int *codeword, float *noisy)
+{
+    if (!c || !c->src.ready || c->src.B < 1) { ctx_err(c, "nbgpu_source_download: no generated batch"); return NBGPU_EINVAL; }
+    CK(c, cudaSetDevice(c->device));
+    const int B = c->src.B;
+    if (codeword) {
+        std::vector<uint8_t> cw((size_t)B * c->N);
+        CK(c, cudaMemcpyAsync(cw.data(), c->src.d_cw, cw.size(), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < cw.size(); i++) codeword[i] = c->inv_h[cw[i]];
+    }
+    if (noisy) {
+        CK(c, cudaMemcpyAsync(noisy, c->d_in, (size_t)B * c->N * c->logq * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    return NBGPU_OK;
+}
+
+extern "C" int nbgpu_source_results(nbgpu_ctx *c, int *bit_errors, int *synd, int *iters)
+{
+    if (!c || !c->src.ready || c->src.B < 1 || c->resident_B != c->src.B) { ctx_err(c, "nbgpu_source_results: no generated batch"); return NBGPU_EINVAL; }
+    CK(c, cudaSetDevice(c->device));
+    const int B = c->src.B;
+    SrcArgs a = source_args(c, NULL, B);
+    source_errors_kernel<<<B, 256, 0, c->stream>>>(a);
+    CK(c, cudaGetLastError());
+    c->launches += 1;
+    if (bit_errors) CK(c, cudaMemcpyAsync(bit_errors, c->src.d_bit_errors, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (synd) CK(c, cudaMemcpyAsync(synd, c->d_synd, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (iters) CK(c, cudaMemcpyAsync(iters, c->d_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return NBGPU_OK;
 }
 
 extern "C" int nbgpu_get_state(nbgpu_ctx *c, int frame, float *APP, float *CtoV)

@@ -341,17 +341,23 @@ float nbgpu_sigma(const nbgpu_code *c, float EbN)
     return (float)sqrt(1.0 / (2.0 * c->rate * pow(10, EbN / 10.0)));                    /* channel.c:51 */
 }
 
-int nbgpu_awgn_bpsk_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin, float EbN, float *noisy)
+/* one sample of channel.c:59; also the host recomputation of the samples the device source flags (nbldpc_source.cuh) */
+float nbgpu_noise_sample(float sigma, float u, float v, int bit)
 {
     const double pi = 3.1415926536;                                                     /* channel.c:18 */
+    const int s = 1 - 2 * bit;
+    return (float)(s + sigma * sqrt(-2.0 * log(u)) * cos(2.0 * pi * v));
+}
+
+int nbgpu_awgn_bpsk_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin, float EbN, float *noisy)
+{
     const float sigma = nbgpu_sigma(c, EbN);
     const int cnt = c->N * c->logq;
     int i;
     for (i = 0; i < cnt; i++) {
         float u = draw_float(r);
         float v = draw_float(r);
-        int s = 1 - 2 * (nbin ? nbin[i] : 0);
-        noisy[i] = (float)(s + sigma * sqrt(-2.0 * log(u)) * cos(2.0 * pi * v));          /* channel.c:59 */
+        noisy[i] = nbgpu_noise_sample(sigma, u, v, nbin ? nbin[i] : 0);
     }
     return NBGPU_OK;
 }
@@ -375,6 +381,21 @@ int nbgpu_accumulate_stats(const nbgpu_code *c, const int *codeword_bits, const 
         stats[4] += iters[f];
         stats[3] += e;
         if (e) { stats[1] += 1; if (synd[f] == 0) stats[2] += 1; }
+        if (stats[1] == 40) stats[5] = 1;
+    }
+    return NBGPU_OK;
+}
+
+/* the same rule fed with per-frame error counts (nbgpu_source_results) */
+int nbgpu_accumulate_results(const int *bit_errors, const int *synd, const int *iters, int B, long *stats)
+{
+    int f;
+    for (f = 0; f < B; f++) {
+        if (stats[5]) break;
+        stats[0] += 1;
+        stats[4] += iters[f];
+        stats[3] += bit_errors[f];
+        if (bit_errors[f]) { stats[1] += 1; if (synd[f] == 0) stats[2] += 1; }
         if (stats[1] == 40) stats[5] = 1;
     }
     return NBGPU_OK;

@@ -39,6 +39,8 @@ void nbgpu_free_schedule(nbgpu_schedule *s);
 void nbgpu_set_global_error(const char *fmt, ...);
 const char *nbgpu_get_global_error(void);
 
+float nbgpu_noise_sample(float sigma, float u, float v, int bit);          /* channel.c:59, one sample */
+
 /* syndrome_ems configuration table (syndrome_decoder.c:1542, 1661, 2285); returns malloc'd [size*dc] */
 int *nbgpu_build_config_table(int dc, int d1, int d2, int d3, int trunc, int *size_out);
 

@@ -55,10 +55,12 @@ def gather_rows(rows):
     return np.concatenate(out, axis=0) if out is not None else None
 
 
-def monte_carlo(code, frames, ebn, decode, batch=256, rank=0, world=1, max_err_frames=40):
+def monte_carlo(code, frames, ebn, decode=None, batch=256, rank=0, world=1, max_err_frames=40, decoder=None):
     """The reference's Monte-Carlo loop (NB_LDPC.c:250-511) sharded by frame block over `world` ranks.
 
-    decode(noisy[B, N, logq], sigma) -> (decide[B, N], synd[B], iters[B]) is the rank's decoder (Decoder.decode_noisy).
+    Either decode(noisy[B, N, logq], sigma) -> (decide[B, N], synd[B], iters[B]) with frames made by the host source
+    (Decoder.decode_noisy), or decoder=<Decoder>: frames are generated, decoded and scored on the rank's GPU
+    (nbgpu_source_frames / nbgpu_run / nbgpu_source_results) and only 12 bytes per frame reach the host.
     Returns on rank 0 the dict of the reference's statistics, None on the other ranks."""
     lo, hi = frame_range(frames, rank, world)
     D = draws_per_frame(code)
@@ -70,6 +72,11 @@ def monte_carlo(code, frames, ebn, decode, batch=256, rank=0, world=1, max_err_f
     rows = np.zeros((hi - lo, 3), np.int64)
     for b0 in range(lo, hi, batch):
         b1 = min(hi, b0 + batch)
+        if decoder is not None:
+            decoder.source_frames(b0, b1 - b0, ebn)
+            decoder.run()
+            rows[b0 - lo:b1 - lo] = np.stack(decoder.source_results(), axis=1)
+            continue
         bits, noisy = [], []
         for _ in range(b0, b1):
             _, nbin = code.random_codeword()

@@ -147,6 +147,25 @@ int nbgpu_geometry(const nbgpu_ctx *ctx, int *geo);
 /* selection rows that needed the exact (slow) scan since creation; diagnostic */
 long nbgpu_slow_selects(nbgpu_ctx *ctx);
 
+/* Frame source on the DEVICE: frames [frame0, frame0 + B) of the reference's Monte-Carlo stream are
+ * produced where the decoder reads them, so a simulation never moves a frame across PCIe.  Replaces, per frame,
+ * RandomBinaryGenerator (tools.c:124-136), Encoding (tools.c:232-270; the elimination of tools.c:151-218 is done once
+ * on the host by nbgpu_code_prepare_encoder) and the noise of ModelChannel_AWGN_BPSK (channel.c:51-62).
+ * `origin` is the drand48 state before frame 0 (nbgpu_rng_reference_default for the reference's stream).
+ * The samples are bit-identical to nbgpu_random_codeword + nbgpu_awgn_bpsk_noise: the few samples whose f32 rounding
+ * could depend on the last bits of the device's log/cos are detected and recomputed by the host's libm
+ * (nbgpu_source_fixups tells how many in the last call).  Afterwards the batch is resident as after
+ * nbgpu_upload_noisy: call nbgpu_run, then nbgpu_source_results (or nbgpu_download for the decisions). */
+int  nbgpu_source_frames(nbgpu_ctx *ctx, nbgpu_code *code, const nbgpu_rng *origin, uint64_t frame0, int B, float EbN);
+/* what the source produced (either may be NULL): codeword symbols [B][N] (CodeWord of tools.c:258), noisy [B][N][logq] */
+int  nbgpu_source_download(nbgpu_ctx *ctx, int *codeword, float *noisy);
+/* after nbgpu_run: information-bit errors of each frame (NB_LDPC.c:479-485), syndrome value, iteration count;
+ * feed them to the frame-order statistics rule (NB_LDPC.c:474-507).  12 bytes per frame cross PCIe. */
+int  nbgpu_source_results(nbgpu_ctx *ctx, int *bit_errors, int *synd, int *iters);
+long nbgpu_source_fixups(const nbgpu_ctx *ctx);
+/* test hook: relative width of the "ambiguous rounding" test (default 2^-46, i.e. 64 ulp of a double) */
+int  nbgpu_source_set_margin(nbgpu_ctx *ctx, double margin);
+
 /* Parity/debug: APP[N][q] and CtoV[E][q] (dense, as decoder_t.APP / decoder_t.CtoV) of one frame of
  * the last batch.  Only frames whose working set is still resident can be read (NBGPU_ESTATE). */
 int nbgpu_get_state(nbgpu_ctx *ctx, int frame, float *APP, float *CtoV);
@@ -170,6 +189,8 @@ int nbgpu_decision_syndrome(nbgpu_ctx *ctx, const float *app, int *decide, int *
  * sum_it, stop flag (1 once the 40th erroneous frame was reached; later frames are ignored). */
 int nbgpu_accumulate_stats(const nbgpu_code *c, const int *codeword_bits, const int *decide,
                            const int *synd, const int *iters, int B, long *stats);
+/* the same rule fed with the per-frame error counts of nbgpu_source_results */
+int nbgpu_accumulate_results(const int *bit_errors, const int *synd, const int *iters, int B, long *stats);
 
 /* build information */
 const char *nbgpu_version(void);

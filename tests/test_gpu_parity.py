@@ -460,8 +460,9 @@ KNOWN = [  # args of the reference binary, console (undetected, err frames, fram
 ]
 
 
+@pytest.mark.parametrize("source", [1, 0], ids=["device_source", "host_source"])
 @pytest.mark.parametrize("args,ecn,console,nfile", KNOWN)
-def test_c_driver_reproduces_reference_console_and_results_file(args, ecn, console, nfile, tmp_path):
+def test_c_driver_reproduces_reference_console_and_results_file(args, ecn, console, nfile, source, tmp_path):
     import re
     import subprocess
     exe = os.path.join(os.path.dirname(nbldpc.LIB_PATH), "nbldpc_mc")
@@ -469,7 +470,7 @@ def test_c_driver_reproduces_reference_console_and_results_file(args, ecn, conso
     os.makedirs(tmp_path / "data")
     a = list(args)
     a[2] = matrix_path(a[2])
-    r = subprocess.run([exe] + a + ["128", "0", str(ecn)], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run([exe] + a + ["128", "0", str(ecn), str(source)], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
     m = re.findall(r"<(\d+)> FER=\s*(\d+)\s*/\s*(\d+)\s*=\s*[\d.]+\s*BER=\s*(\d+)\s*/\s*x\s*=\s*[\d.eE+-]+\s*avr_it=([\d.]+)", r.stdout)
     assert m, r.stdout[-2000:]
@@ -489,6 +490,8 @@ def test_sharded_monte_carlo_on_the_gpu():
     st = multigpu.monte_carlo(code, 2000, 3.0, d.decode_noisy, batch=256)
     assert (st["err_frames"], st["frames"], st["bit_errors"], st["frames_in_results_file"]) == (24, 2000, 153, 2001)
     assert "%.2f" % (st["sum_it"] / st["frames"]) == "1.56"
+    st2 = multigpu.monte_carlo(code, 2000, 3.0, batch=200, decoder=d)                      # frames made on the device
+    assert st2 == st
     # the two halves of a 2-rank run, computed one after the other, give the same per-frame rows
     lo = multigpu.monte_carlo(code, 2000, 3.0, d.decode_noisy, batch=256, rank=0, world=1)
     assert lo == st
