@@ -330,6 +330,25 @@ def ours(args, rank, local_rank, world):
     e2e_val = frames_total / e2e_s * code.info_bits / 1e6
     assert (out[0] == d_res).all() and (out[2] == it_res).all(), "e2e and resident runs disagree"
 
+    # ---------------- whole simulation step on the device: frame source -> decode -> error count ----------------
+    sim = None
+    if not args.no_also:
+        dec.source_frames(rank * B, B, ebn)
+        dec.run(); dec.source_results()
+        nsim = min(args.steps, 3)
+        barrier()
+        s0 = time.perf_counter()
+        for i in range(nsim):
+            dec.source_frames((world * (i + 1) + rank) * B, B, ebn)
+            dec.run()
+            dec.source_results()
+        sim_s = maxr(time.perf_counter() - s0)
+        barrier()
+        sim = {"value": world * B * nsim / sim_s * code.info_bits / 1e6, "unit": "Mbit/s", "steps": nsim, "ms_per_step": 1e3 * sim_s / nsim,
+               "d2h_bytes_per_step": 12 * B, "h2d_bytes_per_step": 0, "host_fixups_last_step": dec.source_fixups(),
+               "note": "Monte-Carlo step with the frames of the reference's drand48 stream generated, decoded (fixed iterations) and scored on the "
+                       "device: nbgpu_source_frames + nbgpu_run + nbgpu_source_results"}
+
     # ---------------- counters: one NCCL all-reduce (the only collective of the path) ----------------
     bit_err = int((bits[:, :code.K, :] != np.stack([code_bits(code, d_res[:, k]) for k in range(code.K)], axis=1)).sum()) if args.count_errors else -1
     counters = np.array([B, int((s_res != 0).sum()), int(it_res.sum()), bit_err], np.int64)
@@ -364,7 +383,7 @@ def ours(args, rank, local_rank, world):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                              "kernel": "decode_kernel<%d, closed, %s>" % (code.q, "syndrome_ems" if args.ecn == "syndrome" else "CheckPassLogEMS"), "kernel_ms": kernel_ms, "bytes_per_frame": bpf, "frames_per_launch": B},
-                "clocks": clocks,
+                "clocks": clocks, "simulation": sim,
                 "counters": {"frames_per_step": int(counters[0]), "frames_nonzero_syndrome": int(counters[1]), "sum_iterations": int(counters[2]),
                              "slow_path_selects": dec.slow_selects()}}
         if world == 1 and args.ecn == "bubble" and not args.no_also and n_m in SYND and code.dc_min == code.dc_max and 4 <= code.dc_max <= 8:

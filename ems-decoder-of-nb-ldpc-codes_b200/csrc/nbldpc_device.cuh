@@ -273,8 +273,9 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
  * (5 instructions per round: redux, setp, predicated st/ld/add).  The NE independent REDUX chains are
  * interleaved so that their latencies overlap.  A result is accepted only if (a) no value was
  * negative/NaN/Inf, (b) adjacent winners (including the (n_m+1)-th) differ in their kept bits, (c) the
- * n_m winners are < 1e5.  Otherwise that edge re-runs the exact scan (same semantics as the reference
- * loop).
+ * n_m winners are < 1e5.  If only (b) fails and not at the n_m boundary, the winners are re-ordered in
+ * place with full comparisons; otherwise that edge re-runs the exact scan (same semantics as the
+ * reference loop).
  *
  * scr[e]: SCR_WORDS u32 of warp-private scratch (free on entry, free on return); sel[e]: 36 u32.
  * Result: lane k < n_m holds (out_llr[e], out_sym[e]) = k-th entry of edge e.
@@ -346,7 +347,27 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         int sym = int(mine & uint32_t(Q - 1));
         float val = reinterpret_cast<const float *>(scr[e])[sym];
         const bool over = lane < n_m && !(val < NB_SENT);
-        if (__any_sync(NB_FULL, bad[e] || amb || over)) {
+        const unsigned ambs = __ballot_sync(NB_FULL, amb);
+        if (ambs && !(ambs >> (n_m - 1)) && !__any_sync(NB_FULL, bad[e] || over)) {
+            /* winners whose kept bits coincide, none of them at the n_m boundary: the SET is right (equal kept bits are
+             * contiguous in key order), only the order inside such runs needs the full (value, symbol) comparison --
+             * odd-even transposition over the n_m lanes until nothing moves */
+            bool moved;
+            do {
+                moved = false;
+#pragma unroll
+                for (int par = 0; par < 2; par++) {
+                    const bool left = (lane & 1) == par;
+                    const int partner = left ? lane + 1 : lane - 1;
+                    const float pv = __shfl_sync(NB_FULL, val, partner & 31);
+                    const int ps = __shfl_sync(NB_FULL, sym, partner & 31);
+                    const bool less = pv < val || (pv == val && ps < sym);
+                    const bool sw = lane < n_m && partner >= 0 && partner < n_m && (left ? less : !less);
+                    if (sw) { val = pv; sym = ps; }
+                    moved |= sw;
+                }
+            } while (__any_sync(NB_FULL, moved));
+        } else if (ambs || __any_sync(NB_FULL, bad[e] || over)) {
             /* exact scan, NB_LDPC.c:356-369 */
             if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
             float tmp[VPL];
