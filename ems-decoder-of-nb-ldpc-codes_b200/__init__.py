@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NBLDPC_B200_LIB") or os.path.join(HERE, "libnbldpc_b200.so")   # override: tuning builds only
 
 OK, EINVAL, EIO, ENOMEM, ECUDA, ESTATE, ERANK = 0, -1, -2, -3, -4, -5, -6
-ALIST_AUTO, ALIST_UBS, ALIST_KN = 0, 1, 2
+ALIST_AUTO, ALIST_UBS, ALIST_KN, ALIST_FULL = 0, 1, 2, 3
 
 _ip = C.POINTER(C.c_int)
 _fp = C.POINTER(C.c_float)

@@ -115,66 +115,143 @@ static int check_graph(const struct nbgpu_code *c)
     return NBGPU_OK;
 }
 
+/* All integers of the file.  The three layouts differ only in how the integers after "N M GF" are arranged:
+ *   UBS  (init.c:195-207)  col degrees | row degrees | E columns (0-based) | E coefficients (symbols 1..q-1)
+ *   KN   (init.c:211-227)  col degrees | row degrees | per row: (column 1-based, exponent 0..q-2) pairs
+ *   FULL (matrices/KN/N64800_*, which the reference cannot read)
+ *                          dv_max dc_max | col degrees | row degrees | per column: (row, exponent) pairs |
+ *                          per row: (column 1-based, exponent) pairs; lists may be zero-padded to the maximum degree */
+static int read_ints(FILE *f, int **out, size_t *count)
+{
+    size_t cap = 1 << 16, n = 0;
+    int *t = malloc(sizeof(int) * cap), v;
+    if (!t) return NBGPU_ENOMEM;
+    while (fscanf(f, "%d", &v) == 1) {
+        if (n == cap) { cap *= 2; int *t2 = realloc(t, sizeof(int) * cap); if (!t2) { free(t); return NBGPU_ENOMEM; } t = t2; }
+        t[n++] = v;
+    }
+    *out = t; *count = n;
+    return NBGPU_OK;
+}
+
+/* FULL layout: returns 1 and fills row_deg/col/val when the token stream fits it, 0 otherwise */
+static int parse_full_alist(struct nbgpu_code *c, const int *t, size_t T)
+{
+    const int N = c->N, M = c->M;
+    if (T < (size_t)5 + N + M) return 0;
+    const int dv = t[3], dc = t[4];
+    const int *cd = t + 5, *rd = t + 5 + N;
+    long Ec = 0, Er = 0;
+    int n, m, k, mx;
+    for (mx = 0, n = 0; n < N; n++) { if (cd[n] < 0 || cd[n] > dv) return 0; Ec += cd[n]; if (cd[n] > mx) mx = cd[n]; }
+    if (mx != dv) return 0;
+    for (mx = 0, m = 0; m < M; m++) { if (rd[m] < 0 || rd[m] > dc) return 0; Er += rd[m]; if (rd[m] > mx) mx = rd[m]; }
+    if (mx != dc || Ec != Er) return 0;
+    const size_t exact = (size_t)5 + N + M + 4 * (size_t)Er, padded = (size_t)5 + N + M + 2 * ((size_t)N * dv + (size_t)M * dc);
+    if (T != exact && T != padded) return 0;
+    const int pad = (T != exact);
+    const int *cols = t + 5 + N + M;
+    const int *rows = cols + (pad ? 2 * (size_t)N * dv : 2 * (size_t)Ec);
+    {   /* the column lists must describe the same matrix as the row lists (only the row lists are kept) */
+        size_t cpos = 0, rpos = 0;
+        size_t *rstart = malloc(sizeof(size_t) * M);
+        int ok = rstart != NULL;
+        for (m = 0; ok && m < M; m++) { rstart[m] = rpos; rpos += pad ? 2 * (size_t)dc : 2 * (size_t)rd[m]; }
+        for (n = 0; ok && n < N; n++) {
+            const int *cl = cols + (pad ? 2 * (size_t)n * dv : cpos);
+            cpos += 2 * (size_t)cd[n];
+            for (k = 0; ok && k < cd[n]; k++) {
+                const int r = cl[2 * k] - 1, e = cl[2 * k + 1];
+                int found = 0, j;
+                if (r < 0 || r >= M) { ok = 0; break; }
+                for (j = 0; j < rd[r]; j++) if (rows[rstart[r] + 2 * j] == n + 1 && rows[rstart[r] + 2 * j + 1] == e) found = 1;
+                if (!found) ok = 0;
+            }
+        }
+        free(rstart);
+        if (!ok) return 0;
+    }
+    c->row_deg = malloc(sizeof(int) * M);
+    memcpy(c->row_deg, rd, sizeof(int) * M);
+    finish_graph(c);
+    c->E = c->row_ptr[M];
+    c->col = malloc(sizeof(int) * c->E);
+    c->val = malloc(sizeof(int) * c->E);
+    for (m = 0; m < M; m++) {
+        const int *r = rows + (pad ? 2 * (size_t)m * dc : 2 * (size_t)c->row_ptr[m]);
+        for (k = 0; k < rd[m]; k++) { c->col[c->row_ptr[m] + k] = r[2 * k] - 1; c->val[c->row_ptr[m] + k] = r[2 * k + 1] + 1; }
+    }
+    return 1;
+}
+
 int nbgpu_code_load(nbgpu_code **out, const char *path, int dialect)
 {
     *out = NULL;
     FILE *f = fopen(path, "r");
     if (!f) { nbgpu_set_global_error("cannot open matrix file '%s'", path); return NBGPU_EIO; }
     struct nbgpu_code *c = calloc(1, sizeof *c);
-    int rc = NBGPU_EIO, n, m, k;
-    int *coldeg = NULL, *rest = NULL;
-    if (fscanf(f, "%d %d %d", &c->N, &c->M, &c->q) != 3 || c->N <= 0 || c->M <= 0 || c->M > c->N) {
-        nbgpu_set_global_error("'%s': bad alist header", path); goto fail;
-    }
+    int rc = NBGPU_EIO, n, k;
+    int *tok = NULL;
+    size_t T = 0;
+    if ((rc = read_ints(f, &tok, &T)) != NBGPU_OK) { nbgpu_set_global_error("out of memory reading '%s'", path); goto fail; }
+    rc = NBGPU_EIO;
+    if (T < 3 || tok[0] <= 0 || tok[1] <= 0 || tok[1] > tok[0]) { nbgpu_set_global_error("'%s': bad alist header", path); goto fail; }
+    c->N = tok[0]; c->M = tok[1]; c->q = tok[2];
     c->logq = (int)rint(log((double)c->q) / log(2.0));                 /* init.c:160-163 */
     if ((1 << c->logq) != c->q || !field_poly(c->q)) {
         nbgpu_set_global_error("GF(%d) is not supported (16, 64, 256 only, as init.c:431)", c->q); rc = NBGPU_EINVAL; goto fail;
     }
     c->K = c->N - c->M;
     c->rate = (float)(c->N - c->M) / c->N;                             /* init.c:167 */
-    coldeg = malloc(sizeof(int) * c->N);
-    for (n = 0; n < c->N; n++) if (fscanf(f, "%d", &coldeg[n]) != 1) { nbgpu_set_global_error("'%s': truncated column degrees", path); goto fail; }
-    c->row_deg = malloc(sizeof(int) * c->M);
-    for (m = 0; m < c->M; m++) if (fscanf(f, "%d", &c->row_deg[m]) != 1 || c->row_deg[m] < 0) { nbgpu_set_global_error("'%s': truncated row degrees", path); goto fail; }
-    finish_graph(c);
-    c->E = c->row_ptr[c->M];
-    rest = malloc(sizeof(int) * 2 * (size_t)c->E);
-    for (k = 0; k < 2 * c->E; k++) if (fscanf(f, "%d", &rest[k]) != 1) { nbgpu_set_global_error("'%s': truncated edge list (%d of %d values)", path, k, 2 * c->E); goto fail; }
-    if (dialect == NBGPU_ALIST_AUTO) {
-        /* a dialect is plausible when all values are in range and the column degrees of the header are met */
-        int ok_ubs = 1, ok_kn = 1;
-        int *cnt = calloc(c->N, sizeof(int));
-        for (k = 0; k < c->E && ok_ubs; k++) {
-            if (rest[k] < 0 || rest[k] >= c->N || rest[c->E + k] < 1 || rest[c->E + k] >= c->q) ok_ubs = 0; else cnt[rest[k]]++;
+    if ((dialect == NBGPU_ALIST_AUTO || dialect == NBGPU_ALIST_FULL) && parse_full_alist(c, tok, T)) dialect = NBGPU_ALIST_FULL;
+    else if (dialect == NBGPU_ALIST_FULL) { nbgpu_set_global_error("'%s': not a full alist file (degree sums or length do not fit)", path); rc = NBGPU_EINVAL; goto fail; }
+    else {
+        if (T < (size_t)3 + c->N + c->M) { nbgpu_set_global_error("'%s': truncated degree lists", path); goto fail; }
+        const int *coldeg = tok + 3;
+        c->row_deg = malloc(sizeof(int) * c->M);
+        for (n = 0; n < c->M; n++) { c->row_deg[n] = tok[3 + c->N + n]; if (c->row_deg[n] < 0) { nbgpu_set_global_error("'%s': negative row degree", path); goto fail; } }
+        finish_graph(c);
+        c->E = c->row_ptr[c->M];
+        const int *rest = tok + 3 + c->N + c->M;
+        if (T < (size_t)3 + c->N + c->M + 2 * (size_t)c->E) {
+            nbgpu_set_global_error("'%s': truncated edge list (%zu of %d values)", path, T - 3 - c->N - c->M, 2 * c->E); goto fail;
         }
-        for (n = 0; n < c->N && ok_ubs; n++) if (cnt[n] != coldeg[n]) ok_ubs = 0;
-        memset(cnt, 0, sizeof(int) * c->N);
-        for (k = 0; k < c->E && ok_kn; k++) {
-            if (rest[2 * k] < 1 || rest[2 * k] > c->N || rest[2 * k + 1] < 0 || rest[2 * k + 1] > c->q - 2) ok_kn = 0; else cnt[rest[2 * k] - 1]++;
+        if (dialect == NBGPU_ALIST_AUTO) {
+            /* a dialect is plausible when all values are in range and the column degrees of the header are met */
+            int ok_ubs = 1, ok_kn = 1;
+            int *cnt = calloc(c->N, sizeof(int));
+            for (k = 0; k < c->E && ok_ubs; k++) {
+                if (rest[k] < 0 || rest[k] >= c->N || rest[c->E + k] < 1 || rest[c->E + k] >= c->q) ok_ubs = 0; else cnt[rest[k]]++;
+            }
+            for (n = 0; n < c->N && ok_ubs; n++) if (cnt[n] != coldeg[n]) ok_ubs = 0;
+            memset(cnt, 0, sizeof(int) * c->N);
+            for (k = 0; k < c->E && ok_kn; k++) {
+                if (rest[2 * k] < 1 || rest[2 * k] > c->N || rest[2 * k + 1] < 0 || rest[2 * k + 1] > c->q - 2) ok_kn = 0; else cnt[rest[2 * k] - 1]++;
+            }
+            for (n = 0; n < c->N && ok_kn; n++) if (cnt[n] != coldeg[n]) ok_kn = 0;
+            free(cnt);
+            if (ok_ubs == ok_kn) {
+                nbgpu_set_global_error("'%s': cannot tell the alist dialect (%s); pass NBGPU_ALIST_UBS, NBGPU_ALIST_KN or NBGPU_ALIST_FULL",
+                                       path, ok_ubs ? "both fit" : "neither fits");
+                rc = NBGPU_EINVAL; goto fail;
+            }
+            dialect = ok_ubs ? NBGPU_ALIST_UBS : NBGPU_ALIST_KN;
         }
-        for (n = 0; n < c->N && ok_kn; n++) if (cnt[n] != coldeg[n]) ok_kn = 0;
-        free(cnt);
-        if (ok_ubs == ok_kn) {
-            nbgpu_set_global_error("'%s': cannot tell the alist dialect (%s); pass NBGPU_ALIST_UBS or NBGPU_ALIST_KN",
-                                   path, ok_ubs ? "both fit" : "neither fits");
-            rc = NBGPU_EINVAL; goto fail;
+        c->col = malloc(sizeof(int) * c->E);
+        c->val = malloc(sizeof(int) * c->E);
+        for (k = 0; k < c->E; k++) {
+            if (dialect == NBGPU_ALIST_KN) { c->col[k] = rest[2 * k] - 1; c->val[k] = rest[2 * k + 1] + 1; }   /* init.c:218-221 */
+            else { c->col[k] = rest[k]; c->val[k] = rest[c->E + k]; }                                          /* init.c:197-205 */
         }
-        dialect = ok_ubs ? NBGPU_ALIST_UBS : NBGPU_ALIST_KN;
     }
     c->dialect = dialect;
-    c->col = malloc(sizeof(int) * c->E);
-    c->val = malloc(sizeof(int) * c->E);
-    for (k = 0; k < c->E; k++) {
-        if (dialect == NBGPU_ALIST_KN) { c->col[k] = rest[2 * k] - 1; c->val[k] = rest[2 * k + 1] + 1; }   /* init.c:218-221 */
-        else { c->col[k] = rest[k]; c->val[k] = rest[c->E + k]; }                                          /* init.c:197-205 */
-    }
     if ((rc = check_graph(c)) != NBGPU_OK) goto fail;
     if ((rc = make_tables(c, NULL, NULL, NULL, NULL)) != NBGPU_OK) goto fail;
-    free(coldeg); free(rest); fclose(f);
+    free(tok); fclose(f);
     *out = c;
     return NBGPU_OK;
 fail:
-    free(coldeg); free(rest); fclose(f);
+    free(tok); fclose(f);
     nbgpu_code_free(c);
     return rc;
 }

@@ -41,6 +41,8 @@ typedef struct nbgpu_code nbgpu_code;
 #define NBGPU_ALIST_AUTO 0
 #define NBGPU_ALIST_UBS  1   /* init.c:195-207 : all columns (0-based) then all coefficients (1..q-1) */
 #define NBGPU_ALIST_KN   2   /* init.c:211-227 : per row (col 1-based, exponent 0..q-2) pairs          */
+#define NBGPU_ALIST_FULL 3   /* full alist (max-degree line, column lists, then row lists of (col 1-based, exponent) pairs):
+                                matrices/KN/N64800_*, which the reference's LoadCode cannot read */
 
 /* replaces LoadCode (init.c:143) + LoadTables (init.c:427).  The alist dialect is a runtime switch
  * instead of the compile-time '#define KN_matrix' (init.c:25). */

@@ -112,3 +112,27 @@ def write_alist_ubs(path, a):
         e = 0
         for m in range(M):
             f.write(" ".join(str(x) for x in a["val"][e:e + a["row_deg"][m]]) + "\n"); e += a["row_deg"][m]
+
+
+def write_alist_full(path, a, pad=False):
+    """full alist: max-degree line, column lists then row lists of (index 1-based, exponent) pairs (matrices/KN/N64800_*);
+    pad=True fills every list with '0 0' pairs up to the maximum degree, as MacKay's tools do for irregular codes"""
+    N, M, q = a["N"], a["M"], a["q"]
+    rd = np.asarray(a["row_deg"]); col = np.asarray(a["col"]); val = np.asarray(a["val"])
+    rp = np.concatenate([[0], np.cumsum(rd)])
+    cols = [[] for _ in range(N)]
+    for m in range(M):
+        for e in range(rp[m], rp[m + 1]):
+            cols[col[e]].append((m + 1, val[e] - 1))
+    cd = [len(c) for c in cols]
+    dv, dc = max(cd), int(rd.max())
+    with open(path, "w") as f:
+        f.write("%d %d %d\n%d %d\n" % (N, M, q, dv, dc))
+        f.write(" ".join(map(str, cd)) + "\n" + " ".join(map(str, rd)) + "\n")
+        for c in cols:
+            items = c + ([(0, 0)] * (dv - len(c)) if pad else [])
+            f.write("   ".join("%d %d" % it for it in items) + "\n")
+        for m in range(M):
+            items = [(col[e] + 1, val[e] - 1) for e in range(rp[m], rp[m + 1])]
+            items += [(0, 0)] * (dc - len(items)) if pad else []
+            f.write("   ".join("%d %d" % it for it in items) + "\n")

@@ -333,6 +333,26 @@ def test_chunked_end_to_end_path_equals_single_launch():
     o.close(); d.close()
 
 
+def test_full_alist_dvb_size_code_equals_oracle(tmp_path):
+    """matrices/KN/N64800_K48600_GF256.txt (full alist, rate 3/4 over GF(256), check degree 8): the reference cannot load it;
+    the oracle port gets the same graph through a UBS copy"""
+    code = nbldpc.Code(matrix_path("matrices/KN/N64800_K48600_GF256.txt"))
+    a = dict(N=code.N, M=code.M, q=code.q, row_deg=code.row_deg, col=code.col, val=code.val)
+    p = str(tmp_path / "ubs")
+    write_alist_ubs(p, a)
+    o = ol.Oracle(p)
+    d = nbldpc.Decoder(code, 20, 25, 10, 0.3, max_batch=6)
+    d.source_frames(0, 6, 3.6)
+    _, noisy = d.source_download()
+    d.run()
+    dec, synd, it = d.download()
+    sigma = code.sigma(3.6)
+    for f in (0, 5):
+        r = o.decode_frame(o.channel_llr(noisy[f], sigma), 20, 25, 10, 0.3)
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"] and it[f] == r["iters"]
+    o.close(); d.close()
+
+
 def test_contexts_with_different_geometries_coexist():
     """two decoders of the same kernel (GF(64), closed form) but different shared-memory plans, used alternately"""
     c1 = nbldpc.Code(matrix_path("matrices/N96_K48_GF64")); c2 = nbldpc.Code(matrix_path("matrices/Mat24_N480_M240"))

@@ -10,7 +10,7 @@ import pytest
 
 import nbldpc
 import oracle_lib as ol
-from common import Golden, golden_names, matrix_path, oracle_frames, product_frames, random_regular_code, write_alist_ubs, ROOT
+from common import Golden, golden_names, matrix_path, oracle_frames, product_frames, random_regular_code, write_alist_full, write_alist_ubs, ROOT
 
 
 def test_library_exports_every_declared_symbol():
@@ -59,6 +59,53 @@ def test_same_code_in_both_dialects():
     b = nbldpc.Code(matrix_path("matrices/KN/N96_K48_GF64.txt"))
     assert a.dialect == 1 and b.dialect == 2
     assert (a.col == b.col).all() and (a.val == b.val).all()
+
+
+def _irregular_code(rng, q):
+    dcs = [int(x) for x in rng.choice([2, 3, 4, 6], 9)]
+    N = 20
+    cols, vals = [], []
+    for dc in dcs:
+        cols += [int(x) for x in rng.choice(N, dc, replace=False)]
+        vals += [int(x) for x in rng.integers(1, q, dc)]
+    return dict(N=N, M=len(dcs), q=q, row_deg=np.array(dcs, np.int32), col=np.array(cols, np.int32), val=np.array(vals, np.int32))
+
+
+@pytest.mark.parametrize("pad", [False, True])
+def test_full_alist_layout(tmp_path, pad):
+    """the layout of matrices/KN/N64800_* (LoadCode of the reference cannot read it), exact and zero-padded"""
+    a = _irregular_code(np.random.default_rng(11), 64)
+    p = str(tmp_path / "full")
+    write_alist_full(p, a, pad=pad)
+    for dialect in (nbldpc.ALIST_AUTO, nbldpc.ALIST_FULL):
+        c = nbldpc.Code(p, dialect=dialect)
+        assert c.dialect == nbldpc.ALIST_FULL and (c.row_deg == a["row_deg"]).all() and (c.col == a["col"]).all() and (c.val == a["val"]).all()
+        assert (c.dc_min, c.dc_max) == (2, 6)
+    # a column list that contradicts the row lists is not accepted as this layout
+    txt = open(p).read().split("\n")
+    li = next(i for i in range(4, 4 + a["N"]) if len(txt[i].split()) >= 2 and txt[i].split()[0] != "0")
+    first = txt[li].split()
+    first[1] = str((int(first[1]) + 1) % 63)
+    txt[li] = " ".join(first)
+    open(p, "w").write("\n".join(txt))
+    with pytest.raises(nbldpc.NbgpuError):
+        nbldpc.Code(p, dialect=nbldpc.ALIST_FULL)
+    with pytest.raises(nbldpc.NbgpuError):
+        nbldpc.Code(p)
+
+
+def test_shipped_full_alist_matrix_loads_and_encodes():
+    c = nbldpc.Code(matrix_path("matrices/KN/N64800_K48600_GF256.txt"))
+    assert (c.dialect, c.N, c.M, c.q, c.dc_min, c.dc_max) == (nbldpc.ALIST_FULL, 8100, 2025, 256, 8, 8)
+    c.prepare_encoder()
+    cw, _ = c.random_codeword()
+    _, add, mul, _ = c.tables()
+    prod = mul[c.val, cw[c.col]]                              # every check sums to zero (GF addition through the table)
+    for m in range(0, c.M, 7):
+        s = 0
+        for x in prod[c.row_ptr[m]:c.row_ptr[m + 1]]:
+            s = add[s, x]
+        assert s == 0
 
 
 def test_loader_errors(tmp_path):
