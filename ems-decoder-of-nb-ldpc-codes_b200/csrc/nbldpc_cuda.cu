@@ -36,7 +36,8 @@
 #include <vector>
 
 #ifndef NT_MAX
-#define NT_MAX 384        /* threads per CTA (upper bound; the plan may use fewer warps) */
+#define NT_MAX 384
+#define NT_SYND 256              /* syndrome check node: at most 8 warps per CTA (its shared memory allows 7 at 945 configurations), 128 registers */        /* threads per CTA (upper bound; the plan may use fewer warps) */
 #endif
 #ifndef CTAS_PER_SM
 #define CTAS_PER_SM 2      /* resident CTAs per SM the decode kernel is compiled for (register cap 65536 / (NT_MAX * CTAS_PER_SM)) */
@@ -295,7 +296,7 @@ __device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t
 }
 
 template <int Q, bool CLOSED, int ECN>
-__global__ void __launch_bounds__(NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs a)
+__global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs a)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -974,7 +975,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     int nw = getenv("NBGPU_WARPS") ? atoi(getenv("NBGPU_WARPS")) : NT_MAX / 32, cpw = getenv("NBGPU_CPW") ? atoi(getenv("NBGPU_CPW")) : 8;
     /* the register budget is what limits residency: keep all NT_MAX/32 warps and shrink the tile before dropping warps */
     if (p->ecn_kind == 1 && !getenv("NBGPU_CPW")) cpw = 4;       /* nodes of a tile are processed one after the other: no shared-memory cost */
-    nw = std::max(1, std::min(nw, NT_MAX / 32)); cpw = std::max(1, std::min(cpw, 32));
+    nw = std::max(1, std::min(nw, (p->ecn_kind == 1 ? NT_SYND : NT_MAX) / 32)); cpw = std::max(1, std::min(cpw, 32));
     if (p->cns_per_step > 0) cpw = std::max(1, std::min(cpw, (p->cns_per_step + nw - 1) / nw));
     for (;;) {
         plan_smem(k, nw, cpw);
