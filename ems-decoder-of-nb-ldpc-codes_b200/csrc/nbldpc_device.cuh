@@ -308,6 +308,23 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         nxt[e] = smem_u32(scr[e] + 32 + lane);
         selp[e] = smem_u32(sel[e]);
     }
+    if constexpr (Q == 16 && NE == 2) {
+        /* GF(16): a row is one key per lane of a half warp.  Both edges are sorted at once, edge 0 in lanes 0-15 and edge 1 in
+         * lanes 16-31, by a 16-wide bitonic network (10 exchanges) instead of 2 x 16 reduction rounds. */
+        const uint32_t other = __shfl_sync(NB_FULL, head[1], lane & 15);
+        uint32_t x = lane < 16 ? head[0] : other;
+#pragma unroll
+        for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const uint32_t y = __shfl_xor_sync(NB_FULL, x, j);
+                const bool up = (k == 16) || ((lane & k) == 0);
+                const bool lower = (lane & j) == 0;
+                x = (lower == up) ? min(x, y) : max(x, y);
+            }
+        }
+        (lane < 16 ? sel[0] : sel[1])[lane & 15] = x;
+    } else {
     /* no __syncwarp needed: every lane only reads back what it wrote itself */
 #define NB_SEL_ROUND(E, OFF)                                                                                   \
     asm volatile("{\n\t"                                                                                        \
@@ -334,6 +351,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
     for (; r < rounds; r++) {
 #pragma unroll
         for (int e = 0; e < NE; e++) { NB_SEL_ROUND(e, 0); selp[e] += 4; }
+    }
     }
     __syncwarp();
 #pragma unroll
