@@ -365,6 +365,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         int sym = int(mine & uint32_t(Q - 1));
         float val = reinterpret_cast<const float *>(scr[e])[sym];
         const bool over = lane < n_m && !(val < NB_SENT);
+        if (__any_sync(NB_FULL, bad[e] || amb || over)) {                      /* rare: one vote on the common path */
         const unsigned ambs = __ballot_sync(NB_FULL, amb);
         if (ambs && !(ambs >> (n_m - 1)) && !__any_sync(NB_FULL, bad[e] || over)) {
             /* winners whose kept bits coincide, none of them at the n_m boundary: the SET is right (equal kept bits are
@@ -385,7 +386,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                     moved |= sw;
                 }
             } while (__any_sync(NB_FULL, moved));
-        } else if (ambs || __any_sync(NB_FULL, bad[e] || over)) {
+        } else {
             /* exact scan, NB_LDPC.c:356-369 */
             if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
             float tmp[VPL];
@@ -401,6 +402,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                 for (int j = 0; j < VPL; j++) if (bg == lane * VPL + j) tmp[j] = NB_SENT;   /* NB_LDPC.c:368 */
                 if (lane == k) { val = bv; sym = bg; }
             }
+        }
         }
         const float v0 = __shfl_sync(NB_FULL, val, 0);
         out_llr[e] = (lane == 0) ? 0.0f : __fsub_rn(val, v0);                               /* NB_LDPC.c:372-373 */
