@@ -300,7 +300,11 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
 {
     constexpr int VPL = QTraits<Q>::VPL;
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+    /* read once through volatile asm: otherwise the register allocator re-reads SR_TID (S2R, ~10 per check node) instead of
+     * keeping the lane number in a register */
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
     WarpMem<Q> wm(smem, a, warp);
     const Lists &ls = wm.ls;
     GFTab gf;
