@@ -273,8 +273,9 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
  * finite floats the bit pattern is monotone in the value, so key order == (value, symbol) order except
  * when two values differ only in the log2(q) dropped mantissa bits.  Each lane sorts its VPL keys with
  * a register network and parks them in shared memory ([rank][lane], row VPL = +inf); n_m+1 rounds of
- * one REDUX.MIN over the lane heads pop the global minimum, the owning lane fetching its next key
- * (5 instructions per round: redux, setp, predicated st/ld/add).  The NE independent REDUX chains are
+ * one REDUX.MIN over the lane heads pop the global minimum, the owning lane stepping to its next row;
+ * every lane then re-reads its head row, so the load needs no predicate and no copy
+ * (5 instructions per round: redux, setp, predicated st/add, ld).  The NE independent REDUX chains are
  * interleaved so that their latencies overlap.  A result is accepted only if (a) no value was
  * negative/NaN/Inf, (b) adjacent winners (including the (n_m+1)-th) differ in their kept bits, (c) the
  * n_m winners are < 1e5.  If only (b) fails and not at the n_m boundary, the winners are re-ordered in
@@ -306,10 +307,10 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         sort_keys<VPL>(key);
         bad[e] = active && key[VPL - 1] >= 0x7f800000u;
 #pragma unroll
-        for (int j = 1; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
+        for (int j = 0; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
         scr[e][VPL * 32 + lane] = NB_KEY_INF;
         head[e] = key[0];
-        nxt[e] = smem_u32(scr[e] + 32 + lane);
+        nxt[e] = smem_u32(scr[e] + lane);              /* row of the lane's current head */
         selp[e] = smem_u32(sel[e]);
     }
     if constexpr (Q == 16 && NE == 2) {
@@ -337,8 +338,8 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                  "redux.sync.min.u32 m, %0, 0xffffffff;\n\t"                                                    \
                  "setp.eq.u32 p, %0, m;\n\t"                                                                    \
                  "@p st.shared.u32 [%2+" #OFF "], %0;\n\t"                                                      \
-                 "@p ld.shared.u32 %0, [%1];\n\t"                                                               \
                  "@p add.u32 %1, %1, 128;\n\t"                                                                  \
+                 "ld.shared.u32 %0, [%1];\n\t"                                                                  \
                  "}"                                                                                             \
                  : "+r"(head[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
     int r = 0;
