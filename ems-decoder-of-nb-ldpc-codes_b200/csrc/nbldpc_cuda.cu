@@ -295,6 +295,141 @@ __device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t
     if (p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * GF(16): a row is 16 values, so one warp carries TWO edges of a check node side by side -- edge t in
+ * lanes 0-15, edge t+1 in lanes 16-31, lane & 15 = symbol / list entry -- instead of two half-empty
+ * instruction streams.  Same arithmetic, same order of operations as the generic phases below.
+ * ---------------------------------------------------------------------------------------------- */
+template <bool CLOSED>
+__device__ __forceinline__ void gf16_phase1(const WarpMem<16> &wm, const GFTab &gf, int c, int e0, int dc, int dcm, float *app_f,
+                                            const uint8_t *ctov_f, const uint32_t *einfo, int n_m, int rs, int lane, unsigned *slow_counter)
+{
+    const Lists &ls = wm.ls;
+    const int h = lane >> 4, idx = lane & 15, hb = lane & 16;
+    const RecLane rlh(n_m, idx, rs);
+    float *scr = reinterpret_cast<float *>(h ? wm.scr[1] : wm.scr[0]);
+    const int rounds = n_m + 1 < 16 ? n_m + 1 : 16;
+    for (int t = 0; t < dc; t += 2) {
+        const int te = min(t + h, dc - 1);                       /* t+h >= dc: duplicate of the last edge, nothing stored */
+        const bool valid = t + h < dc;
+        const uint32_t ei = wm.ew[c * dcm + te];
+        const int hv = (ei >> 20) & 0xff;
+        float *prow = app_f + (size_t)((ei & 0xfffffu) * 16u);
+        float v = prow[idx];
+        const RecView r = load_record(ctov_f, (uint32_t)(e0 + te), rlh);
+        if (NB_L2_PREFETCH && t + 2 < dc) prefetch_edges<16>(app_f, ctov_f, einfo, e0 + t + 2, min(2, dc - t - 2), rs, lane);
+        scr[idx] = r.sat;                                        /* dense CtoV row, bubble_decoder.c:262-270 */
+        __syncwarp();
+        if (idx < r.stp) scr[r.sym] = r.llr;
+        __syncwarp();
+        const float cv = scr[idx];
+        __syncwarp();
+        v = __fsub_rn(v, cv);                                    /* NB_LDPC.c:334 */
+        if (valid) prow[idx] = v;                                /* parked for phase 3 */
+        /* truncation, NB_LDPC.c:354-374: unique keys, 16-wide bitonic sort inside each half */
+        uint32_t x = (__float_as_uint(v) & ~15u) | (uint32_t)idx;
+        const bool bad = x >= 0x7f800000u;
+#pragma unroll
+        for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const uint32_t y = __shfl_xor_sync(NB_FULL, x, j);
+                const bool up = (k == 16) || ((lane & k) == 0);
+                const bool lower = (lane & j) == 0;
+                x = (lower == up) ? min(x, y) : max(x, y);
+            }
+        }
+        const uint32_t after = __shfl_down_sync(NB_FULL, x, 1);
+        const bool amb = idx < n_m && idx + 1 < rounds && ((x >> 4) == (after >> 4));
+        int sym = (int)(x & 15u);
+        float val = __shfl_sync(NB_FULL, v, hb | sym);
+        const bool over = idx < n_m && !(val < NB_SENT);
+        const unsigned flags = __ballot_sync(NB_FULL, bad || amb || over);
+        if (flags) {                                             /* rare: exact scan, NB_LDPC.c:356-369, one half at a time */
+            for (int hh = 0; hh < 2; hh++) {
+                if (!((flags >> (16 * hh)) & 0xffffu)) continue;
+                if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
+                float tmp = __shfl_sync(NB_FULL, v, 16 * hh + idx);          /* both halves hold a copy of the row */
+                for (int k = 0; k < n_m; k++) {
+                    float bv = NB_SENT; int bg = 0x7fffffff;
+                    if (tmp < bv) { bv = tmp; bg = idx; }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(NB_FULL, bv, o);
+                        const int og = __shfl_xor_sync(NB_FULL, bg, o);
+                        if (ov < bv || (ov == bv && og < bg)) { bv = ov; bg = og; }
+                    }
+                    if (bg == 0x7fffffff) bg = 0;                              /* nothing below 1e5: (1e5, symbol 0) */
+                    if (bg == idx) tmp = NB_SENT;                              /* NB_LDPC.c:368 */
+                    if (h == hh && idx == k) { val = bv; sym = bg; }
+                }
+            }
+        }
+        const float v0 = __shfl_sync(NB_FULL, val, hb);
+        const float llr = idx == 0 ? 0.0f : __fsub_rn(val, v0);               /* NB_LDPC.c:372-373 */
+        if (valid) {
+            const uint32_t list = ls.in(c, t + h);
+            if (idx < n_m) {
+                sts_f32(list + 4 * idx, llr);
+                sts_u8(ls.sym(list) + idx, (uint32_t)gf_rot_in<16, CLOSED>(gf, sym, hv));   /* bubble_decoder.c:145 */
+            }
+            if (idx == 0) sts_u8(ls.len(list), (uint32_t)n_m);
+        }
+    }
+}
+
+template <bool CLOSED>
+__device__ __forceinline__ void gf16_phase3(const WarpMem<16> &wm, const GFTab &gf, int c, int e0, int dc, int dcm, float *app_f,
+                                            uint8_t *ctov_f, uint8_t *dec_f, int n_m, int rs, float offset, int lane)
+{
+    const Lists &ls = wm.ls;
+    const int h = lane >> 4, idx = lane & 15, hb = lane & 16;
+    const RecLane rlh(n_m, idx, rs);
+    float *scr = reinterpret_cast<float *>(h ? wm.scr3[1] : wm.scr3[0]);
+    for (int t = 0; t < dc; t += 2) {
+        const int te = min(t + h, dc - 1);
+        const bool valid = t + h < dc;
+        const uint32_t ei = wm.ew[c * dcm + te];
+        const uint32_t var = ei & 0xfffffu;
+        float *prow = app_f + (size_t)(var * 16u);
+        float v = prow[idx];                                     /* the Mvc row parked by phase 1 */
+        /* record entry of this lane and saturation constant, bubble_decoder.c:231-264 */
+        const uint32_t list = ls.at(c, id_out(dc, te), dc);
+        const int len = (int)lds_u8(ls.len(list));
+        RecView nr;
+        nr.stp = len; nr.llr = NB_SENT; nr.sym = 0;
+        if (idx < len) {
+            nr.llr = lds_f32(list + 4 * idx);
+            nr.sym = gf_rot_out<16, CLOSED>(gf, (int)lds_u8(ls.sym(list) + idx), (ei >> 20) & 0xff);
+        }
+        const float last = __shfl_sync(NB_FULL, nr.llr, hb | max(len - 1, 0));
+        nr.sat = __fadd_rn(len > 0 ? last : NB_SENT, offset);
+        if (valid) {                                             /* NB_LDPC.c:438 */
+            uint8_t *rec = ctov_f + (size_t)(uint32_t)(e0 + te) * rlh.stride;
+            if (idx < n_m) { *reinterpret_cast<float *>(rec + rlh.llr) = nr.llr; rec[rlh.sym] = (uint8_t)nr.sym; }
+            if (idx == 0) *reinterpret_cast<int2 *>(rec + rlh.tail) = make_int2(__float_as_int(nr.sat), nr.stp);
+        }
+        scr[idx] = nr.sat;
+        __syncwarp();
+        if (idx < len) scr[nr.sym] = nr.llr;
+        __syncwarp();
+        const float mcv = scr[idx];
+        __syncwarp();
+        v = __fadd_rn(mcv, v);                                   /* NB_LDPC.c:448 */
+        if (valid) prow[idx] = v;
+        /* Decision, tools.c:312-330: strict '<' from 1e5, ties -> lowest symbol, default 0 */
+        float bv = NB_SENT; int bg = 0x7fffffff;
+        if (v < bv) { bv = v; bg = idx; }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(NB_FULL, bv, o);
+            const int og = __shfl_xor_sync(NB_FULL, bg, o);
+            if (ov < bv || (ov == bv && og < bg)) { bv = ov; bg = og; }
+        }
+        if (valid && (ei >> 28) && idx == 0) dec_f[var] = (uint8_t)(bg == 0x7fffffff ? 0 : bg);
+    }
+}
+
 template <int Q, bool CLOSED, int ECN>
 __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs a)
 {
@@ -389,6 +524,13 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                     float *app_f = app + mt.z * frame_app;
                     const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
                     if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
+                    if constexpr (Q == 16 && NE == 2) {
+                        if (NB_L2_PREFETCH && c + 1 < cnt) {
+                            const int4 nx = wm.meta[c + 1];
+                            if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
+                        }
+                        gf16_phase1<CLOSED>(wm, gf, c, e0, dc, dcm, app_f, ctov_f, a.einfo, n_m, rs, lane, a.slow_counter);
+                    } else
                     for (int t = 0; t < dc; t += NE) {
                         float v[NE][VPL];
                         RecView r[NE];
@@ -444,6 +586,9 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                     float *app_f = app + mt.z * frame_app;
                     uint8_t *ctov_f = ctov + mt.z * frame_ctov;
                     uint8_t *dec_f = dec + mt.z * N;
+                    if constexpr (Q == 16 && NE == 2) {
+                        gf16_phase3<CLOSED>(wm, gf, c, e0, dc, dcm, app_f, ctov_f, dec_f, n_m, rs, a.offset, lane);
+                    } else
                     for (int t = 0; t < dc; t += NE) {
                         float v[NE][VPL];
                         uint32_t ei[NE];
