@@ -1126,6 +1126,28 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     if (p->ecn_kind == 1 && !getenv("NBGPU_CPW")) cpw = 4;       /* nodes of a tile are processed one after the other: no shared-memory cost */
     nw = std::max(1, std::min(nw, (p->ecn_kind == 1 ? NT_SYND : NT_MAX) / 32)); cpw = std::max(1, std::min(cpw, 32));
     if (p->cns_per_step > 0) cpw = std::max(1, std::min(cpw, (p->cns_per_step + nw - 1) / nw));
+    if (p->ecn_kind == 0 && !getenv("NBGPU_WARPS") && !getenv("NBGPU_CPW") && p->cns_per_step <= 0) {
+        /* Pick (warps, nodes per warp) among the plans that fit.  Cost of one tile in instructions: phases 1/3 grow with the
+         * tile (dc edges per node, heavier for larger q), the ElementarySteps do not as long as the tile's 4 task slots per
+         * node fit the 32 lanes -- so high-degree codes want bigger tiles even at the price of fewer warps, whose
+         * latency-hiding value is the measured `eff` (Ahmed_64800_R34_GF16: (12,4) 196, (10,5) 209, (8,6) 217, (6,8) 208 Mbit/s;
+         * KN N64800_K48600_GF256: (8,4) 213, (12,3) 205). */
+        static const double eff[13] = { 0, .2, .35, .5, .6, .7, .77, .84, .90, .925, .95, .975, 1.0 };
+        const double w_edge = k.q == 16 ? 175.0 : k.q == 64 ? 330.0 : 660.0;
+        const int dc = code->dc_max, rounds = dc - 2 + (dc > 4 ? 1 : 0);
+        const double es_round = 70.0 * (k.n_m + 5) * (k.q > 64 ? 1.1 : 1.0);   /* ~n_m+5 pops of ~70 issue slots; q = 256 keeps its mask in shared memory */
+        double best = -1.0; int bnw = 0, bcpw = 0;
+        for (int w = NT_MAX / 32; w >= 1; w -= (w > 6 || best < 0 ? 2 : 6))          /* 12, 10, 8, 6 -- smaller only if nothing fits */
+            for (int cw = 8; cw >= 1; cw--) {
+                plan_smem(k, w, cw);
+                if (k.smem_bytes > budget) continue;
+                const double tile = cw * dc * w_edge + std::max(rounds, 1) * es_round * ((cw * 4 + 31) / 32);
+                const double score = eff[w] * cw / tile;
+                if (score > best * 1.0001) { best = score; bnw = w; bcpw = cw; }
+            }
+        if (bnw) { nw = bnw; cpw = bcpw; }
+        plan_smem(k, nw, cpw);
+    } else
     for (;;) {
         plan_smem(k, nw, cpw);
         if (k.smem_bytes <= budget) break;
