@@ -136,3 +136,15 @@ def write_alist_full(path, a, pad=False):
             items = [(col[e] + 1, val[e] - 1) for e in range(rp[m], rp[m + 1])]
             items += [(0, 0)] * (dc - len(items)) if pad else []
             f.write("   ".join("%d %d" % it for it in items) + "\n")
+
+
+def write_alist_kn(path, a):
+    """KN dialect (init.c:211-227): degrees, then per row (column 1-based, exponent) pairs"""
+    N, M, q = a["N"], a["M"], a["q"]
+    rd = np.asarray(a["row_deg"]); col = np.asarray(a["col"]); val = np.asarray(a["val"])
+    rp = np.concatenate([[0], np.cumsum(rd)])
+    with open(path, "w") as f:
+        f.write("%d %d %d\n\n" % (N, M, q))
+        f.write(" ".join(map(str, np.bincount(col, minlength=N))) + "\n" + " ".join(map(str, rd)) + "\n\n")
+        for m in range(M):
+            f.write("   ".join("%d %d" % (col[e] + 1, val[e] - 1) for e in range(rp[m], rp[m + 1])) + "\n")

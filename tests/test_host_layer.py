@@ -10,7 +10,7 @@ import pytest
 
 import nbldpc
 import oracle_lib as ol
-from common import Golden, golden_names, matrix_path, oracle_frames, product_frames, random_regular_code, write_alist_full, write_alist_ubs, ROOT
+from common import Golden, golden_names, matrix_path, oracle_frames, product_frames, random_regular_code, write_alist_full, write_alist_kn, write_alist_ubs, ROOT
 
 
 def test_library_exports_every_declared_symbol():
@@ -92,6 +92,23 @@ def test_full_alist_layout(tmp_path, pad):
         nbldpc.Code(p, dialect=nbldpc.ALIST_FULL)
     with pytest.raises(nbldpc.NbgpuError):
         nbldpc.Code(p)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_three_layouts_of_one_random_code_load_identically(tmp_path, seed):
+    rng = np.random.default_rng(100 + seed)
+    a = _irregular_code(rng, int(rng.choice([16, 64, 256])))
+    codes = []
+    for name, writer, dialect in (("u", write_alist_ubs, nbldpc.ALIST_UBS), ("k", write_alist_kn, nbldpc.ALIST_KN),
+                                  ("f", write_alist_full, nbldpc.ALIST_FULL), ("p", lambda p, x: write_alist_full(p, x, pad=True), nbldpc.ALIST_FULL)):
+        p = str(tmp_path / name)
+        writer(p, a)
+        c = nbldpc.Code(p)                               # dialect detected from the file
+        assert c.dialect == dialect, name
+        codes.append(c)
+    for c in codes:
+        assert (c.row_deg == a["row_deg"]).all() and (c.col == a["col"]).all() and (c.val == a["val"]).all()
+        assert (c.tables()[1] == codes[0].tables()[1]).all()
 
 
 def test_shipped_full_alist_matrix_loads_and_encodes():
@@ -203,6 +220,15 @@ def test_statistics_follow_reference_rules():
         c.accumulate_stats(bits[lo:lo + 64], dec[lo:lo + 64], synd[lo:lo + 64], it[lo:lo + 64], stats)
     assert ref[1] == 40 and stats[5] == 1
     assert [int(x) for x in stats[:5]] == [ref[0], ref[1], ref[2], ref[3], ref[4]]
+    # the same rule fed with per-frame error counts (what nbgpu_source_results delivers), other batch size
+    bing = c.tables()[0]
+    err = np.array([(bing[dec[f, :c.K]] != bits[f].reshape(c.N, c.logq)[:c.K]).sum() for f in range(frames)], np.int32)
+    stats2 = np.zeros(6, np.int64)
+    for lo in range(0, frames, 50):
+        e, sy, itr = (np.ascontiguousarray(x[lo:lo + 50], np.int32) for x in (err, synd, it))
+        assert nbldpc.lib().nbgpu_accumulate_results(e.ctypes.data_as(C.POINTER(C.c_int)), sy.ctypes.data_as(C.POINTER(C.c_int)),
+                                                     itr.ctypes.data_as(C.POINTER(C.c_int)), len(e), stats2.ctypes.data_as(C.POINTER(C.c_long))) == 0
+    assert (stats2 == stats).all()
     o.close()
 
 
