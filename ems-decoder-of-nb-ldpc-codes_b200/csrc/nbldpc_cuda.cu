@@ -9,20 +9,24 @@
  * runs them through three warp-private phases (no CTA barrier in between, lists in the warp's own
  * shared memory):
  *
- *   phase 1  warp per edge, NE edges interleaved:  Mvc = APP - CtoV (NB_LDPC.c:334), parked in the APP row;
- *            top-n_m selection + normalisation (:354-374), rotation by the edge coefficient (bubble_decoder.c:133)
+ *   phase 1  warp per edge, NE edges interleaved:  Mvc = APP - CtoV (NB_LDPC.c:334); top-n_m selection +
+ *            normalisation (:354-374), rotation by the edge coefficient (bubble_decoder.c:133)
  *   phase 2  THREAD per ElementaryStep, 4 task slots per check node: forward/backward chains with the
  *            merges folded into the rounds where their inputs are ready (bubble_decoder.c:157-227, 316-593)
- *   phase 3  warp per edge, NE edges interleaved:  parked Mvc reloaded, saturation + offset + expansion to
- *            the dense q-vector (bubble_decoder.c:231-281), CtoV store, APP = Mcv + Mvc (NB_LDPC.c:415-450),
- *            fused Decision (tools.c:312)
+ *   phase 3  warp per edge, NE edges interleaved:  Mvc again (parked in the APP row by phase 1, NB_PARK_MVC = 1, or
+ *            recomputed from the untouched APP row and the old record, NB_PARK_MVC = 0), saturation + offset +
+ *            expansion to the dense q-vector (bubble_decoder.c:231-281), CtoV store, APP = Mcv + Mvc
+ *            (NB_LDPC.c:415-450), fused Decision (tools.c:312)
  * With ecn = 1 the tile is processed one check node at a time through the syndrome-based node (nbldpc_synd.cuh).
+ *
+ * The kernel is bound by the shared/global wavefront pipe of the SM (l1tex data stage), not by HBM or issue slots
+ * (ncu, profiles/): every design choice below trades wavefronts for ALU work -- conflict-free 128-bit row moves,
+ * clean scratch rows instead of fill + scatter, selection winners kept in registers, exact low bits by shuffle.
  *
  * HBM layout per resident frame (slot): APP[N][q] f32 (row = 4q bytes, one coalesced warp access);
  * CtoV as one lossless record per edge {llr[n_m] f32, sat f32, stp i32, sym[n_m] u8} -- a dense CtoV
  * row is "stp explicit (symbol, LLR) pairs + one constant" (bubble_decoder.c:262-270); decisions u8.
- * Every APP row is read and written twice per edge visit (APP -> parked Mvc -> APP); the parked copy is short-lived and
- * is given an evict_last L2 policy, the rest is streamed.  The syndrome-based node stores CtoV as dense rows instead.
+ * The syndrome-based node stores CtoV as dense rows instead.
  */
 #include "nbldpc_device.cuh"
 #include "nbldpc_synd.cuh"
@@ -45,6 +49,10 @@
 #define NE 2              /* edges interleaved per warp in phases 1 and 3 */
 #ifndef NB_L2_PREFETCH
 #define NB_L2_PREFETCH 1   /* phase 1 pulls the next pair's APP rows and records into L2 while the current pair is selected */
+#endif
+
+#ifndef NB_PARK_MVC
+#define NB_PARK_MVC 1      /* 1: phase 1 parks Mvc in the APP row, phase 3 reloads it; 0: phase 3 recomputes it from the APP row + old record */
 #endif
 
 #define UNIT_NT 256       /* block size of the small unit-boundary kernels */
@@ -70,12 +78,14 @@ struct KArgs {
     unsigned *queue, *slow_counter;
     /* shared memory map (bytes): tables | misc | per-warp scratch areas | per-warp lists */
     int off_tab, off_misc, off_wa, wa_bytes, off_wb, wb_bytes;
-    int wa_mask, wa_meta, wa_einfo;     /* offsets inside a warp's small private area: ES mask | tile meta | tile edge words */
-    int wb_scr1, wb_scr3, wb_U, wb_R;   /* offsets inside a warp's list area: phase-1 scratch (scr[NE] | sel[NE]), phase-3
-                                           scratch (scr[NE]), input lists U[cpw][dc_max], other lists R[cpw][L - dc_max].
+    int wa_mask, wa_meta, wa_einfo, wa_len;   /* offsets inside a warp's small private area: ES mask | tile meta | tile edge words | list lengths */
+    int wb_scr1, wb_scr3, wb_U, wb_R;   /* offsets inside a warp's list area: phase-1 scratch (clean rows[NE] | key queues[NE] |
+                                           sel[NE]), phase-3 scratch (clean rows[NE]), input lists U[cpw][dc_max], other lists
+                                           R[cpw][L - dc_max] directly behind them (one array of lists).
                                            Bubble path: the phase-1 scratch aliases R (unused until phase 2) and the phase-3
                                            scratch aliases U (dead after phase 2).                                         */
-    int lstride;                        /* bytes per list: n_m f32 | n_m u8 | len u8 | pad */
+    int lstride;                        /* bytes per list: n_m f32 | n_m u8 | pad; an ODD number of words, so that the lists of a
+                                           tile start in different banks (the ElementarySteps read one list per lane)      */
     int smem_bytes;
     /* syndrome-based check node (ecn = 1): dense CtoV rows, configuration table, per-warp sort buffers */
     int ecn, S, Spad, n_cv;
@@ -84,18 +94,17 @@ struct KArgs {
     int off_cfg, sw_key, sw_pay, sw_gf, sw_hist, sw_M, sw_perm;   /* sw_*: offsets inside a warp's list area */
 };
 
-/* Lists of a warp's tile in shared memory, by 32-bit shared-window address.  c = check node of the
- * tile, li = list id.  One list = n_m f32 LLRs, n_m u8 symbols (binary images), 1 u8 length. */
+/* Lists of a warp's tile in shared memory, by 32-bit shared-window address: one array of cpw * L lists, the input lists
+ * U[c][t] first (index c * dcm + t), then the forward/backward/merge lists R[c][.].  One list = n_m f32 LLRs followed by
+ * n_m u8 symbols (binary images); the lengths live in a byte array of their own. */
 struct Lists {
-    uint32_t baseU, baseR; int lstride, strideU, strideR, n_m;     /* strides per check node */
+    uint32_t base, lenb; int lstride, n_m, dcm, lr, r0;     /* lr = L - dcm lists per node in R, r0 = cpw * dcm */
     /* li < dc: input list of edge li; li >= dc: forward/backward/merge list number li - dc */
-    __device__ __forceinline__ uint32_t at(int c, int li, int dc) const
-    {
-        return li < dc ? baseU + c * strideU + li * lstride : baseR + c * strideR + (li - dc) * lstride;
-    }
-    __device__ __forceinline__ uint32_t in(int c, int t) const { return baseU + c * strideU + t * lstride; }
+    __device__ __forceinline__ int idx(int c, int li, int dc) const { return li < dc ? c * dcm + li : r0 + c * lr + (li - dc); }
+    __device__ __forceinline__ int in(int c, int t) const { return c * dcm + t; }
+    __device__ __forceinline__ uint32_t addr(int i) const { return base + (uint32_t)(i * lstride); }
     __device__ __forceinline__ uint32_t sym(uint32_t list) const { return list + 4 * n_m; }
-    __device__ __forceinline__ uint32_t len(uint32_t list) const { return list + 5 * n_m; }
+    __device__ __forceinline__ uint32_t len(int i) const { return lenb + (uint32_t)i; }
 };
 /* list ids of one node with degree dc: U[t] = t; F after s steps = dc+s-1 (s>=1); B after s steps =
  * dc+(dc-2)+s-1; merge k = dc+2(dc-2)+k  (bubble_decoder.c:166-227: MatriceInter rows) */
@@ -119,9 +128,10 @@ struct TileMeta {
 
 /* a warp's private shared memory */
 template <int Q> struct WarpMem {
-    uint32_t *scr[NE];       /* phase 1, per in-flight edge: sorted keys / dense row                       */
-    uint32_t *sel[NE];       /* phase 1: winners of the selection rounds                                    */
-    uint32_t *scr3[NE];      /* phase 3, per in-flight edge: dense row                                      */
+    float *row[NE];          /* phase 1, per in-flight edge: clean row for the record expansion (bubble path only) */
+    uint32_t *scr[NE];       /* phase 1, per in-flight edge: selection queue (sorted keys)                          */
+    uint32_t *sel[NE];       /* phase 1: winners of the selection rounds (NB_SEL_CAPTURE = 0 / GF(16) half-warp)   */
+    float *row3[NE];         /* phase 3, per in-flight edge: clean row                                              */
     uint32_t mask;           /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided (shared address)  */
     TileMeta meta;           /* [cpw] {first edge | degree << 24 (0 = skip), frame}                         */
     uint32_t *ew;            /* [cpw][dc_max] einfo words of the tile's edges (one coalesced load per tile) */
@@ -130,17 +140,19 @@ template <int Q> struct WarpMem {
     {
         unsigned char *wa = smem + a.off_wa + warp * a.wa_bytes;
         unsigned char *wb = smem + a.off_wb + warp * a.wb_bytes;
+        const int rows = a.ecn == 0 ? NE * Q : 0;          /* floats of clean rows in front of the queues */
 #pragma unroll
         for (int e = 0; e < NE; e++) {
-            scr[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + e * QTraits<Q>::SCR_WORDS;
-            sel[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + NE * QTraits<Q>::SCR_WORDS + e * 36;
-            scr3[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr3) + e * QTraits<Q>::SCR_WORDS;
+            row[e] = reinterpret_cast<float *>(wb + a.wb_scr1) + e * Q;
+            scr[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + rows + e * QTraits<Q>::SCR_WORDS;
+            sel[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + rows + NE * QTraits<Q>::SCR_WORDS + e * 36;
+            row3[e] = reinterpret_cast<float *>(wb + a.wb_scr3) + e * Q;
         }
         mask = smem_u32(wa + a.wa_mask);
         meta.p = reinterpret_cast<int2 *>(wa + a.wa_meta);
         ew = reinterpret_cast<uint32_t *>(wa + a.wa_einfo);
-        ls.baseU = smem_u32(wb + a.wb_U); ls.baseR = smem_u32(wb + a.wb_R);
-        ls.lstride = a.lstride; ls.strideU = a.dc_max * a.lstride; ls.strideR = (a.L - a.dc_max) * a.lstride; ls.n_m = a.n_m;
+        ls.base = smem_u32(wb + a.wb_U); ls.lenb = smem_u32(wa + a.wa_len);
+        ls.lstride = a.lstride; ls.n_m = a.n_m; ls.dcm = a.dc_max; ls.lr = a.L - a.dc_max; ls.r0 = a.cpw * a.dc_max;
     }
 };
 
@@ -167,10 +179,11 @@ __device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const Til
                     a = id_F(dc, k); b = id_B(dc, dc - 3 - k); o = id_M(dc, k);
                 }
                 if (valid) {
-                    const uint32_t la = ls.at(c, a, dc), lb = ls.at(c, b, dc), lo = ls.at(c, o, dc);
-                    const int s = es_serial<Q>(la, ls.sym(la), (int)lds_u8(ls.len(la)), lb, ls.sym(lb), (int)lds_u8(ls.len(lb)),
+                    const int ia = ls.idx(c, a, dc), ib = ls.idx(c, b, dc), io = ls.idx(c, o, dc);
+                    const uint32_t la = ls.addr(ia), lb = ls.addr(ib), lo = ls.addr(io);
+                    const int s = es_serial<Q>(la, ls.sym(la), (int)lds_u8(ls.len(ia)), lb, ls.sym(lb), (int)lds_u8(ls.len(ib)),
                                                lo, ls.sym(lo), mask + 4 * lane, ls.n_m, nb_oper);
-                    sts_u8(ls.len(lo), (uint32_t)s);
+                    sts_u8(ls.len(io), (uint32_t)s);
                 }
             }
             __syncwarp();
@@ -181,17 +194,18 @@ __device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const Til
 /* phase 3 core: from the check node's output list of one edge (binary-image symbols) build the
  * record entry of this lane and the saturation constant (bubble_decoder.c:231-264). */
 template <int Q, bool CLOSED>
-__device__ __forceinline__ RecView finish_list(const Lists &ls, uint32_t list, int h, const GFTab &gf, float offset, int lane)
+__device__ __forceinline__ RecView finish_list(const Lists &ls, int li, int h, const GFTab &gf, float offset, int lane)
 {
     RecView r;
-    const int len = (int)lds_u8(ls.len(list));
+    const uint32_t list = ls.addr(li);
+    const int len = (int)lds_u8(ls.len(li));
     r.stp = len;                                                     /* first absent entry, :233-243 */
     r.llr = NB_SENT; r.sym = 0;
     if (lane < len) {
         r.llr = lds_f32(list + 4 * lane);
         r.sym = gf_rot_out<Q, CLOSED>(gf, (int)lds_u8(ls.sym(list) + lane), h);       /* DIVGF by the coefficient, :249-254 */
     }
-    const float last = __shfl_sync(NB_FULL, r.llr, max(len - 1, 0));
+    const float last = lds_f32(list + 4 * max(len - 1, 0));          /* broadcast read */
     r.sat = __fadd_rn(len > 0 ? last : NB_SENT, offset);             /* :264 (len == 0 cannot occur) */
     return r;
 }
@@ -236,7 +250,7 @@ __device__ __forceinline__ void intake_variable(const float *noisy_n, double den
     for (int h = 0; h < VPL; h++) if (Q >= 32 || lane < Q) row[lane | (h << 5)] = w[h];     /* image index = lane | h << 5 */
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < VPL; j++) v[j] = (Q >= 32 || lane < Q) ? row[img[lane * VPL + j]] : 0.0f;
+    for (int j = 0; j < VPL; j++) v[j] = (Q >= 32 || lane < Q) ? row[img[QTraits<Q>::sym(lane, j)]] : 0.0f;
     __syncwarp();
 }
 
@@ -273,7 +287,7 @@ __device__ __forceinline__ void synd_dense_row(uint32_t out, const GFTab &gf, in
 {
 #pragma unroll
     for (int j = 0; j < QTraits<Q>::VPL; j++) {
-        const int s = lane * QTraits<Q>::VPL + j;
+        const int s = QTraits<Q>::sym(lane, j);
         mcv[j] = (Q >= 32 || lane < Q) ? lds_f32(out + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)) : NB_SENT;
     }
 }
@@ -307,7 +321,7 @@ __device__ __forceinline__ void gf16_phase1(const WarpMem<16> &wm, const GFTab &
     const Lists &ls = wm.ls;
     const int h = lane >> 4, idx = lane & 15, hb = lane & 16;
     const RecLane rlh(n_m, idx, rs);
-    float *scr = reinterpret_cast<float *>(h ? wm.scr[1] : wm.scr[0]);
+    float *scr = h ? wm.row[1] : wm.row[0];
     const int rounds = n_m + 1 < 16 ? n_m + 1 : 16;
     for (int t = 0; t < dc; t += 2) {
         const int te = min(t + h, dc - 1);                       /* t+h >= dc: duplicate of the last edge, nothing stored */
@@ -368,12 +382,13 @@ __device__ __forceinline__ void gf16_phase1(const WarpMem<16> &wm, const GFTab &
         const float v0 = __shfl_sync(NB_FULL, val, hb);
         const float llr = idx == 0 ? 0.0f : __fsub_rn(val, v0);               /* NB_LDPC.c:372-373 */
         if (valid) {
-            const uint32_t list = ls.in(c, t + h);
+            const int li = ls.in(c, t + h);
+            const uint32_t list = ls.addr(li);
             if (idx < n_m) {
                 sts_f32(list + 4 * idx, llr);
                 sts_u8(ls.sym(list) + idx, (uint32_t)gf_rot_in<16, CLOSED>(gf, sym, hv));   /* bubble_decoder.c:145 */
             }
-            if (idx == 0) sts_u8(ls.len(list), (uint32_t)n_m);
+            if (idx == 0) sts_u8(ls.len(li), (uint32_t)n_m);
         }
     }
 }
@@ -385,7 +400,7 @@ __device__ __forceinline__ void gf16_phase3(const WarpMem<16> &wm, const GFTab &
     const Lists &ls = wm.ls;
     const int h = lane >> 4, idx = lane & 15, hb = lane & 16;
     const RecLane rlh(n_m, idx, rs);
-    float *scr = reinterpret_cast<float *>(h ? wm.scr3[1] : wm.scr3[0]);
+    float *scr = h ? wm.row3[1] : wm.row3[0];
     for (int t = 0; t < dc; t += 2) {
         const int te = min(t + h, dc - 1);
         const bool valid = t + h < dc;
@@ -394,8 +409,9 @@ __device__ __forceinline__ void gf16_phase3(const WarpMem<16> &wm, const GFTab &
         float *prow = app_f + (size_t)(var * 16u);
         float v = prow[idx];                                     /* the Mvc row parked by phase 1 */
         /* record entry of this lane and saturation constant, bubble_decoder.c:231-264 */
-        const uint32_t list = ls.at(c, id_out(dc, te), dc);
-        const int len = (int)lds_u8(ls.len(list));
+        const int li = ls.idx(c, id_out(dc, te), dc);
+        const uint32_t list = ls.addr(li);
+        const int len = (int)lds_u8(ls.len(li));
         RecView nr;
         nr.stp = len; nr.llr = NB_SENT; nr.sym = 0;
         if (idx < len) {
@@ -430,6 +446,135 @@ __device__ __forceinline__ void gf16_phase3(const WarpMem<16> &wm, const GFTab &
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Bubble path, q >= 64: phases 1 and 3 of a warp's tile.  Two edges are in flight per warp (NE): their global loads,
+ * shared-memory round trips and REDUX chains interleave.
+ * ---------------------------------------------------------------------------------------------- */
+template <int Q, bool CLOSED>
+__device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm, const GFTab &gf, int cnt, float *app, uint8_t *ctov,
+                                            size_t frame_app, size_t frame_ctov, const RecLane &rl, uint64_t pol_first, uint64_t pol_keep,
+                                            bool minform, int lane)
+{
+    constexpr int VPL = QTraits<Q>::VPL;
+    const Lists &ls = wm.ls;
+    const int dcm = a.dc_max, n_m = a.n_m, rs = a.rec_stride;
+#pragma unroll
+    for (int e = 0; e < NE; e++) fill_row<Q>(wm.row[e], lane, NB_ROW_CLEAN);
+    __syncwarp();
+    for (int c = 0; c < cnt; c++) {
+        const int4 mt = wm.meta[c];
+        const int e0 = mt.x, dc = mt.y;
+        float *app_f = app + mt.z * frame_app;
+        const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
+        if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
+        for (int t = 0; t < dc; t += NE) {
+            float v[NE][VPL];
+            RecView r[NE];
+            int hv[NE];
+            float *prow[NE];
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                const int te = min(t + e, dc - 1);                 /* t+e >= dc: duplicate of the last edge, result ignored */
+                const uint32_t ed = (uint32_t)(e0 + te);
+                const uint32_t ei = wm.ew[c * dcm + te];
+                hv[e] = (ei >> 20) & 0xff;
+                prow[e] = app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q);
+                /* the row comes back in phase 3 (as the parked Mvc or as itself): keep it in L2 */
+                load_row_hint<Q>(prow[e], lane, v[e], NB_PARK_MVC ? pol_first : pol_keep);
+                r[e] = load_record(ctov_f, ed, rl);
+            }
+            /* next pair of edges of the tile -> L2 while this pair is processed */
+            if (!NB_L2_PREFETCH) { }
+            else if (t + NE < dc) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0 + t + NE, min(NE, dc - t - NE), rs, lane);
+            else if (c + 1 < cnt) {
+                const int4 nx = wm.meta[c + 1];
+                if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
+            }
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                float cv[VPL];
+                expand_record<Q>(r[e], lane, wm.row[e], cv, minform);
+#pragma unroll
+                for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
+                if (NB_PARK_MVC && t + e < dc) store_row_hint<Q>(prow[e], lane, v[e], pol_keep);     /* parked for phase 3 (NB_LDPC.c:448 adds this vector) */
+            }
+            float llr[NE]; int sym[NE];
+            uint32_t *scr[NE], *sel[NE];
+#pragma unroll
+            for (int e = 0; e < NE; e++) { scr[e] = wm.scr[e]; sel[e] = wm.sel[e]; }
+            select_edges<Q, NE>(v, lane, scr, sel, n_m, llr, sym, a.slow_counter);
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                if (t + e < dc) {
+                    const int li = ls.in(c, t + e);
+                    const uint32_t list = ls.addr(li);
+                    if (lane < n_m) {
+                        sts_f32(list + 4 * lane, llr[e]);
+                        sts_u8(ls.sym(list) + lane, (uint32_t)gf_rot_in<Q, CLOSED>(gf, sym[e], hv[e]));   /* bubble_decoder.c:145 */
+                    }
+                    if (lane == 0) sts_u8(ls.len(li), (uint32_t)n_m);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int Q, bool CLOSED>
+__device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm, const GFTab &gf, int cnt, float *app, uint8_t *ctov,
+                                            uint8_t *dec, size_t frame_app, size_t frame_ctov, const RecLane &rl, uint64_t pol_first,
+                                            bool minform, bool decide, int lane)
+{
+    constexpr int VPL = QTraits<Q>::VPL;
+    const Lists &ls = wm.ls;
+    const int dcm = a.dc_max, n_m = a.n_m;
+#pragma unroll
+    for (int e = 0; e < NE; e++) fill_row<Q>(wm.row3[e], lane, NB_ROW_CLEAN);
+    __syncwarp();
+    for (int c = 0; c < cnt; c++) {
+        const int4 mt = wm.meta[c];
+        const int e0 = mt.x, dc = mt.y;
+        float *app_f = app + mt.z * frame_app;
+        uint8_t *ctov_f = ctov + mt.z * frame_ctov;
+        uint8_t *dec_f = dec + mt.z * a.N;
+        for (int t = 0; t < dc; t += NE) {
+            float v[NE][VPL];
+            uint32_t ei[NE];
+            RecView old[NE];
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                const int te = min(t + e, dc - 1);
+                ei[e] = wm.ew[c * dcm + te];
+                load_row_hint<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e], pol_first);    /* parked Mvc, or the APP row again */
+                if (!NB_PARK_MVC) old[e] = load_record(ctov_f, (uint32_t)(e0 + te), rl);
+            }
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                if (t + e < dc) {
+                    const uint32_t ed = (uint32_t)(e0 + t + e), var = ei[e] & 0xfffffu;
+                    if (!NB_PARK_MVC) {
+                        float cv[VPL];
+                        expand_record<Q>(old[e], lane, wm.row3[e], cv, minform);
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334, same operands as phase 1 */
+                    }
+                    const RecView nr = finish_list<Q, CLOSED>(ls, ls.idx(c, id_out(dc, t + e), dc), (ei[e] >> 20) & 0xff, gf, a.offset, lane);
+                    store_record(ctov_f, ed, rl, nr, n_m, lane);
+                    float mcv[VPL];
+                    expand_record<Q>(nr, lane, wm.row3[e], mcv, minform);    /* :262-281 */
+#pragma unroll
+                    for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
+                    store_row_hint<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v[e], pol_first);
+                    if (decide && (ei[e] >> 28)) {                                         /* tools.c:312 fused */
+                        const int d = warp_argmin<Q>(v[e], lane);
+                        if (lane == 0) dec_f[var] = (uint8_t)d;
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int Q, bool CLOSED, int ECN>
 __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_kernel(const KArgs a)
 {
@@ -441,7 +586,6 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
     WarpMem<Q> wm(smem, a, warp);
-    const Lists &ls = wm.ls;
     GFTab gf;
     load_gf_tables(smem, a, gf);
     load_cfg_table(smem, a);
@@ -455,6 +599,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
     const size_t frame_app = (size_t)N * Q, frame_ctov = (size_t)a.E * rs;
     const RecLane rl(n_m, lane, rs);
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    const bool minform = a.offset >= 0.0f;
     float *app = a.app + blockIdx.x * F * frame_app;
     uint8_t *ctov = a.ctov + blockIdx.x * F * frame_ctov;
     uint8_t *dec = a.dec + (size_t)blockIdx.x * F * N;
@@ -497,6 +642,8 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
         }
 
         for (int pass = 0; pass < a.passes; pass++) {
+            /* Decision + Syndrom are observable only through the early-termination test and after the last pass */
+            const bool decide = a.early_stop || pass == a.passes - 1;
             for (int st = 0; st < a.nsteps; st++) {
                 const int c0 = a.step_ptr[st], ncn = a.step_ptr[st + 1] - c0;
                 const int items = ncn * nf;                   /* item = f * ncn + ci */
@@ -517,105 +664,31 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                 }
                 __syncwarp();
                 if constexpr (ECN == 0) {
-                /* ---------------- phase 1 ---------------- */
-                for (int c = 0; c < cnt; c++) {
-                    const int4 mt = wm.meta[c];
-                    const int e0 = mt.x, dc = mt.y;
-                    float *app_f = app + mt.z * frame_app;
-                    const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
-                    if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
                     if constexpr (Q == 16 && NE == 2) {
-                        if (NB_L2_PREFETCH && c + 1 < cnt) {
-                            const int4 nx = wm.meta[c + 1];
-                            if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
-                        }
-                        gf16_phase1<CLOSED>(wm, gf, c, e0, dc, dcm, app_f, ctov_f, a.einfo, n_m, rs, lane, a.slow_counter);
-                    } else
-                    for (int t = 0; t < dc; t += NE) {
-                        float v[NE][VPL];
-                        RecView r[NE];
-                        int hv[NE];
-                        float *prow[NE];
-#pragma unroll
-                        for (int e = 0; e < NE; e++) {
-                            const int te = min(t + e, dc - 1);                 /* t+e >= dc: duplicate of the last edge, result ignored */
-                            const uint32_t ed = (uint32_t)(e0 + te);
-                            const uint32_t ei = wm.ew[c * dcm + te];
-                            hv[e] = (ei >> 20) & 0xff;
-                            prow[e] = app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q);
-                            load_row_hint<Q>(prow[e], lane, v[e], pol_stream);
-                            r[e] = load_record(ctov_f, ed, rl);
-                        }
-                        /* next pair of edges of the tile -> L2 while this pair is processed */
-                        if (!NB_L2_PREFETCH) { }
-                        else if (t + NE < dc) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0 + t + NE, min(NE, dc - t - NE), rs, lane);
-                        else if (c + 1 < cnt) {
-                            const int4 nx = wm.meta[c + 1];
-                            if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
-                        }
-#pragma unroll
-                        for (int e = 0; e < NE; e++) {
-                            float cv[VPL];
-                            expand_record<Q>(r[e], lane, reinterpret_cast<float *>(wm.scr[e]), cv);
-#pragma unroll
-                            for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
-                            if (t + e < dc) store_row_hint<Q>(prow[e], lane, v[e], pol_keep);     /* parked for phase 3 (NB_LDPC.c:448 adds this vector) */
-                        }
-                        float llr[NE]; int sym[NE];
-                        select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
-#pragma unroll
-                        for (int e = 0; e < NE; e++) {
-                            if (t + e < dc) {
-                                const uint32_t list = ls.in(c, t + e);
-                                if (lane < n_m) {
-                                    sts_f32(list + 4 * lane, llr[e]);
-                                    sts_u8(ls.sym(list) + lane, (uint32_t)gf_rot_in<Q, CLOSED>(gf, sym[e], hv[e]));   /* bubble_decoder.c:145 */
-                                }
-                                if (lane == 0) sts_u8(ls.len(list), (uint32_t)n_m);
+                        const Lists &ls = wm.ls;
+                        for (int c = 0; c < cnt; c++) {
+                            const int4 mt = wm.meta[c];
+                            const int e0 = mt.x, dc = mt.y;
+                            float *app_f = app + mt.z * frame_app;
+                            const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
+                            if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
+                            if (NB_L2_PREFETCH && c + 1 < cnt) {
+                                const int4 nx = wm.meta[c + 1];
+                                if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
                             }
+                            gf16_phase1<CLOSED>(wm, gf, c, e0, dc, dcm, app_f, ctov_f, a.einfo, n_m, rs, lane, a.slow_counter);
                         }
+                        __syncwarp();
+                        tile_elementary_steps<Q>(ls, wm.meta, cnt, dcm, wm.mask, lane, a.nb_oper);
+                        for (int c = 0; c < cnt; c++) {
+                            const int4 mt = wm.meta[c];
+                            gf16_phase3<CLOSED>(wm, gf, c, mt.x, mt.y, dcm, app + mt.z * frame_app, ctov + mt.z * frame_ctov, dec + mt.z * N, n_m, rs, a.offset, lane);
+                        }
+                    } else {
+                        tile_phase1<Q, CLOSED>(a, wm, gf, cnt, app, ctov, frame_app, frame_ctov, rl, pol_stream, pol_keep, minform, lane);
+                        tile_elementary_steps<Q>(wm.ls, wm.meta, cnt, dcm, wm.mask, lane, a.nb_oper);
+                        tile_phase3<Q, CLOSED>(a, wm, gf, cnt, app, ctov, dec, frame_app, frame_ctov, rl, pol_stream, minform, decide, lane);
                     }
-                }
-                __syncwarp();
-                /* ---------------- phase 2 ---------------- */
-                tile_elementary_steps<Q>(ls, wm.meta, cnt, dcm, wm.mask, lane, a.nb_oper);
-                /* ---------------- phase 3 ---------------- */
-                for (int c = 0; c < cnt; c++) {
-                    const int4 mt = wm.meta[c];
-                    const int e0 = mt.x, dc = mt.y;
-                    float *app_f = app + mt.z * frame_app;
-                    uint8_t *ctov_f = ctov + mt.z * frame_ctov;
-                    uint8_t *dec_f = dec + mt.z * N;
-                    if constexpr (Q == 16 && NE == 2) {
-                        gf16_phase3<CLOSED>(wm, gf, c, e0, dc, dcm, app_f, ctov_f, dec_f, n_m, rs, a.offset, lane);
-                    } else
-                    for (int t = 0; t < dc; t += NE) {
-                        float v[NE][VPL];
-                        uint32_t ei[NE];
-#pragma unroll
-                        for (int e = 0; e < NE; e++) {
-                            ei[e] = wm.ew[c * dcm + min(t + e, dc - 1)];
-                            load_row_hint<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e], pol_stream);    /* the Mvc row parked by phase 1 */
-                        }
-#pragma unroll
-                        for (int e = 0; e < NE; e++) {
-                            if (t + e < dc) {
-                                const uint32_t ed = (uint32_t)(e0 + t + e), var = ei[e] & 0xfffffu;
-                                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t + e), dc), (ei[e] >> 20) & 0xff, gf, a.offset, lane);
-                                store_record(ctov_f, ed, rl, nr, n_m, lane);
-                                float mcv[VPL];
-                                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr3[e]), mcv);    /* :262-281 */
-#pragma unroll
-                                for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
-                                store_row_hint<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v[e], pol_stream);
-                                if (ei[e] >> 28) {                                                     /* tools.c:312 fused */
-                                    const int d = warp_argmin<Q>(v[e], lane);
-                                    if (lane == 0) dec_f[var] = (uint8_t)d;
-                                }
-                            }
-                        }
-                    }
-                }
                 } else {
                     /* ---------------- syndrome-based check node: one node at a time per warp ---------------- */
                     const SyndMem sm = make_synd_mem(smem, a, warp);
@@ -643,7 +716,10 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);
                             }
                             float llr[NE]; int sym[NE];
-                            select_edges<Q, NE>(v, lane, wm.scr, wm.sel, n_m, llr, sym, a.slow_counter);
+                            uint32_t *scr[NE], *sel[NE];
+#pragma unroll
+                            for (int e = 0; e < NE; e++) { scr[e] = wm.scr[e]; sel[e] = wm.sel[e]; }
+                            select_edges<Q, NE>(v, lane, scr, sel, n_m, llr, sym, a.slow_counter);
 #pragma unroll
                             for (int e = 0; e < NE; e++) {
                                 if (t + e < dc && lane < n_m) {
@@ -671,7 +747,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                             for (int j = 0; j < VPL; j++) v[j] = __fadd_rn(mcv[j], __fsub_rn(v[j], cv[j]));   /* NB_LDPC.c:334, 448 */
                             store_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, mcv);                   /* NB_LDPC.c:438 */
                             store_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v);
-                            if (ei >> 28) {
+                            if (decide && (ei >> 28)) {
                                 const int dd = warp_argmin<Q>(v, lane);
                                 if (lane == 0) dec_f[var] = (uint8_t)dd;
                             }
@@ -681,6 +757,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                 }
                 __syncthreads();
             }
+            if (!decide) continue;
             /* ---------------- Syndrom (tools.c:284-299) + early termination (NB_LDPC.c:470) ---------------- */
             for (int i = tid; i < nf; i += nthr) s_badrow[i] = a.M;
             __syncthreads();
@@ -719,7 +796,7 @@ __global__ void __launch_bounds__(UNIT_NT) select_kernel(const float *rows, floa
 {
     constexpr int VPL = QTraits<Q>::VPL;
     constexpr int UW = UNIT_NT / 32;
-    __shared__ uint32_t scr_s[UW][QTraits<Q>::SCR_WORDS + 64];     /* + slack: a lane may read one row past the sentinel */
+    __shared__ uint32_t scr_s[UW][QTraits<Q>::SCR_WORDS + 64];     /* + slack: a lane that popped the +inf row reads one row further */
     __shared__ uint32_t sel_s[UW][36];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *scr[1] = { scr_s[warp] };
@@ -777,24 +854,27 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
         for (int i = lane; i < cnt * dc * n_m; i += 32) {
             const int c = i / (dc * n_m), r = i - c * dc * n_m, t = r / n_m, k = r - t * n_m;
             const size_t src = ((size_t)(b0 + c) * dc + t) * n_m + k;
-            const uint32_t list = ls.in(c, t);
+            const int li = ls.in(c, t);
+            const uint32_t list = ls.addr(li);
             sts_f32(list + 4 * k, vllr[src]);
             sts_u8(ls.sym(list) + k, (uint32_t)gf_rot_in<Q, CLOSED>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]));
-            if (k == 0) sts_u8(ls.len(list), (uint32_t)n_m);
+            if (k == 0) sts_u8(ls.len(li), (uint32_t)n_m);
         }
         if (lane < cnt) wm.meta.set(lane, e0, dc, 0);
         __syncwarp();
         tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
+        fill_row<Q>(wm.row3[0], lane, NB_ROW_CLEAN);       /* aliases the input lists, dead after the elementary steps (degree 2: a region of its own) */
+        __syncwarp();
         for (int c = 0; c < cnt; c++)
             for (int t = 0; t < dc; t++) {
-                const RecView nr = finish_list<Q, CLOSED>(ls, ls.at(c, id_out(dc, t), dc), a.hval[e0 + t], gf, a.offset, lane);
+                const RecView nr = finish_list<Q, CLOSED>(ls, ls.idx(c, id_out(dc, t), dc), a.hval[e0 + t], gf, a.offset, lane);
                 float mcv[VPL];
-                expand_record<Q>(nr, lane, reinterpret_cast<float *>(wm.scr3[0]), mcv);
+                expand_record<Q>(nr, lane, wm.row3[0], mcv, a.offset >= 0.0f);
                 float *dst = cllr + ((size_t)(b0 + c) * dc + t) * Q;
                 store_row<Q>(dst, lane, mcv);
                 int *gdst = cgf + ((size_t)(b0 + c) * dc + t) * Q;
 #pragma unroll
-                for (int j = 0; j < VPL; j++) if (Q >= 32 || lane < Q) gdst[lane * VPL + j] = lane * VPL + j;   /* :276 */
+                for (int j = 0; j < VPL; j++) if (Q >= 32 || lane < Q) gdst[QTraits<Q>::sym(lane, j)] = QTraits<Q>::sym(lane, j);   /* :276 */
             }
         __syncwarp();
     }
@@ -900,10 +980,10 @@ __global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const f
             for (int k = 0; k < Q; k++) {
                 float bv = NB_SENT; int bg = 0x7fffffff;
 #pragma unroll
-                for (int j = 0; j < VPL; j++) if ((Q >= 32 || lane < Q) && tmp[j] < bv) { bv = tmp[j]; bg = lane * VPL + j; }
+                for (int j = 0; j < VPL; j++) if ((Q >= 32 || lane < Q) && tmp[j] < bv) { bv = tmp[j]; bg = QTraits<Q>::sym(lane, j); }
                 warp_lexmin(bv, bg);
 #pragma unroll
-                for (int j = 0; j < VPL; j++) if (bg == lane * VPL + j) tmp[j] = NB_SENT;
+                for (int j = 0; j < VPL; j++) if ((Q >= 32 || lane < Q) && bg == QTraits<Q>::sym(lane, j)) tmp[j] = NB_SENT;
                 if (lane == 0) { illr[r * Q + k] = bv; igf[r * Q + k] = (bg == 0x7fffffff) ? -1 : bg; }
             }
         }
@@ -915,7 +995,8 @@ template <int ECN> static const void *decode_fn_e(int q, int closed)
     if (closed) return q == 16 ? (const void *)decode_kernel<16, true, ECN> : q == 64 ? (const void *)decode_kernel<64, true, ECN> : (const void *)decode_kernel<256, true, ECN>;
     return q == 16 ? (const void *)decode_kernel<16, false, ECN> : q == 64 ? (const void *)decode_kernel<64, false, ECN> : (const void *)decode_kernel<256, false, ECN>;
 }
-static const void *decode_fn(int q, int closed, int ecn) { return ecn ? decode_fn_e<1>(q, closed) : decode_fn_e<0>(q, closed); }
+/* q is validated in nbgpu_create (16, 64 or 256); anything else never reaches a launch */
+static const void *decode_fn(int q, int closed, int ecn) { if (q != 16 && q != 64 && q != 256) return nullptr; return ecn ? decode_fn_e<1>(q, closed) : decode_fn_e<0>(q, closed); }
 static const void *checknode_fn(int q, int closed, int ecn)
 {
     if (ecn) {
@@ -960,6 +1041,8 @@ struct nbgpu_ctx {
         uint64_t D;
         double margin;
         long fixups;
+        uint64_t code_hash;      /* graph + coefficients of the code the encoder tables were built from */
+        int state;               /* 0: nothing generated; 1: batch generated, not decoded; 2: generated batch decoded */
     } src;
     long launches;
     float last_ms;
@@ -978,6 +1061,8 @@ static void ctx_err(nbgpu_ctx *c, const char *fmt, ...)
 }
 #define CK(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx_err(ctx, "%s failed: %s", #call, cudaGetErrorString(e_)); return NBGPU_ECUDA; } } while (0)
 
+extern "C" void nbgpu_destroy(nbgpu_ctx *c);
+static void source_teardown(nbgpu_ctx *c);
 extern "C" const char *nbgpu_last_error(const nbgpu_ctx *ctx) { return ctx ? ctx->err : nbgpu_get_global_error(); }
 
 extern "C" int nbgpu_device_count(void)
@@ -1006,30 +1091,35 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     int off = 0;
     k.off_tab = off; off += 512;
     k.off_misc = off; off += align_up((2 + 3 * k.F) * 4, 16);
-    /* per-warp small area: ES mask (q = 256) | meta */
+    /* per-warp small area: ES mask (q = 256) | meta | edge words | list lengths */
     int wa = 0;
     k.wa_mask = wa; wa += (k.q > 64 && k.ecn == 0) ? 8 * 32 * 4 : 0;
     k.wa_meta = wa; wa += cpw * 8;
     k.wa_einfo = wa; wa += cpw * k.dc_max * 4;
+    k.wa_len = wa; wa += align_up(cpw * k.L, 4);
     k.wa_bytes = align_up(wa, 16);
     k.off_wa = off; off += nw * k.wa_bytes;
-    k.lstride = align_up(5 * k.n_m + 1, 4);
-    const int s3 = NE * scr_words(k.q) * 4, s1 = s3 + NE * 36 * 4;
+    k.lstride = align_up(5 * k.n_m, 4);
+    if (((k.lstride / 4) & 1) == 0) k.lstride += 4;       /* odd number of words: consecutive lists start in different banks */
+    const int s3 = NE * k.q * 4;                                             /* clean rows */
+    const int sq = NE * scr_words(k.q) * 4 + NE * 36 * 4;                     /* selection queues + winners */
     if (k.ecn == 0) {
-        /* per-warp lists: U[cpw][dc_max] | R[cpw][L - dc_max], each list {n_m f32 | n_m u8 | len u8}.  Scratch aliases them. */
-        const int ub = align_up(std::max(cpw * k.dc_max * k.lstride, s3), 16);
-        const int rb = align_up(std::max(cpw * (k.L - k.dc_max) * k.lstride, s1), 16);
-        k.wb_U = 0; k.wb_scr3 = 0; k.wb_R = ub; k.wb_scr1 = ub;
-        k.wb_bytes = ub + rb;
-        if (k.dc_min < 3) { k.wb_scr3 = k.wb_bytes; k.wb_bytes += align_up(s3, 16); }   /* degree 2: the output lists ARE input lists */
+        /* per-warp lists: U[cpw][dc_max] | R[cpw][L - dc_max] as one array, each list {n_m f32 | n_m u8}.  Scratch aliases them. */
+        const int ub = cpw * k.dc_max * k.lstride, rb = cpw * (k.L - k.dc_max) * k.lstride;
+        k.wb_U = 0; k.wb_R = ub;
+        k.wb_scr1 = align_up(ub, 16);                      /* phase-1 scratch over the R lists */
+        int total = std::max(ub + rb, k.wb_scr1 + s3 + sq);
+        if (s3 <= ub && k.dc_min >= 3) k.wb_scr3 = 0;      /* phase-3 rows over the input lists, dead after phase 2 ... */
+        else { k.wb_scr3 = align_up(total, 16); total = k.wb_scr3 + s3; }   /* ... unless they do not fit, or degree 2: the output lists ARE input lists */
+        k.wb_bytes = align_up(total, 16);
     } else {
-        /* syndrome check node: CTA-wide configuration table, then per warp: scratch | lists | keys x2 | payload x2 | gf | hist | M | upd | perm */
+        /* syndrome check node: CTA-wide configuration table, then per warp: lists | scratch/keys x2 | payload x2 | gf | hist | M | perm */
         k.off_cfg = off; off += align_up(k.S * k.dc_max, 16);
         int wb2 = 0;
         k.wb_U = wb2; k.wb_R = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
         /* the selection scratch of phase 1 is dead once the node's lists are written: it aliases the sort buffers */
         k.wb_scr1 = wb2; k.wb_scr3 = wb2;
-        k.sw_key = wb2; wb2 += std::max(2 * std::max(4 * k.Spad, 4096), align_up(s1, 16));
+        k.sw_key = wb2; wb2 += std::max(2 * std::max(4 * k.Spad, 4096), align_up(sq, 16));
         k.sw_pay = wb2; wb2 += 2 * 2 * k.Spad;
         k.sw_gf = wb2; wb2 += k.Spad;
         k.sw_hist = wb2; wb2 += 256 * 4;
@@ -1043,8 +1133,10 @@ static void plan_smem(KArgs &k, int nw, int cpw)
 
 extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu_params *p, int device, int max_batch)
 {
+    if (!out) { ctx_err(NULL, "nbgpu_create: NULL output pointer"); return NBGPU_EINVAL; }
     *out = NULL;
     if (!code || !p) { ctx_err(NULL, "nbgpu_create: NULL argument"); return NBGPU_EINVAL; }
+    if (code->q != 16 && code->q != 64 && code->q != 256) { ctx_err(NULL, "GF(%d): kernels exist for GF(16), GF(64) and GF(256) only (init.c:431-435)", code->q); return NBGPU_EINVAL; }
     if (p->ecn_kind != 0 && p->ecn_kind != 1) { ctx_err(NULL, "ecn_kind %d unknown (0 = CheckPassLogEMS, 1 = syndrome_ems)", p->ecn_kind); return NBGPU_EINVAL; }
     if (p->n_m < 5 || p->n_m > 32 || p->n_m > code->q) { ctx_err(NULL, "n_m=%d unsupported: need 5 <= n_m <= min(q,32) (ElementaryStep reads row 4, bubble_decoder.c:457)", p->n_m); return NBGPU_EINVAL; }
     if (p->nb_iter_max < 2) { ctx_err(NULL, "nb_iter_max must be >= 2 (nb_iter_max-1 passes are run, NB_LDPC.c:314)"); return NBGPU_EINVAL; }
@@ -1059,17 +1151,20 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); ctx_err(NULL, "no CUDA device available (this library has no CPU fallback)"); return NBGPU_ECUDA; }
     if (device < 0 || device >= ndev) { ctx_err(NULL, "device %d out of range (0..%d)", device, ndev - 1); return NBGPU_EINVAL; }
     nbgpu_ctx *c = (nbgpu_ctx *)calloc(1, sizeof *c);
+    if (!c) { ctx_err(NULL, "out of memory"); return NBGPU_ENOMEM; }
+    /* from here on every failure goes through nbgpu_destroy(c), which releases whatever was created so far */
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx_err(NULL, "%s failed: %s", #call, cudaGetErrorString(e_)); cudaGetLastError(); nbgpu_destroy(c); return NBGPU_ECUDA; } } while (0)
     c->device = device; c->p = *p; c->max_batch = max_batch;
     c->N = code->N; c->M = code->M; c->E = code->E; c->q = code->q; c->logq = code->logq; c->dc_max = code->dc_max;
-    CK(c, cudaSetDevice(device));
+    CKF(cudaSetDevice(device));
     cudaDeviceProp prop;
-    CK(c, cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) { ctx_err(c, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); free(c); return NBGPU_ECUDA; }
-    CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; i++) { CK(c, cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming)); CK(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)); }
-    CK(c, cudaEventCreate(&c->ev0)); CK(c, cudaEventCreate(&c->ev1));
-    CK(c, cudaEventCreate(&c->ev_t0)); CK(c, cudaEventCreate(&c->ev_t1));
+    CKF(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { ctx_err(c, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); nbgpu_destroy(c); return NBGPU_ECUDA; }
+    CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKF(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) { CKF(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming)); CKF(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)); }
+    CKF(cudaEventCreate(&c->ev0)); CKF(cudaEventCreate(&c->ev1));
+    CKF(cudaEventCreate(&c->ev_t0)); CKF(cudaEventCreate(&c->ev_t1));
 
     const int q = code->q, E = code->E, N = code->N, M = code->M;
     KArgs &k = c->k;
@@ -1205,11 +1300,11 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     const void *fn = decode_fn(q, k.gf_closed, k.ecn);
     /* opt in to the device maximum, not to this context's size: the attribute is per function and several contexts with
      * different geometries may share a kernel */
-    CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CKF(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     const void *fn2 = checknode_fn(q, k.gf_closed, k.ecn);
-    CK(c, cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CKF(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     int per_sm = 0;
-    CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, k.nw * 32, k.smem_bytes, cudaOccupancyDefault));
+    CKF(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, k.nw * 32, k.smem_bytes, cudaOccupancyDefault));
     if (per_sm < 1) { ctx_err(c, "decode kernel does not fit on an SM (smem %d bytes)", k.smem_bytes); nbgpu_destroy(c); return NBGPU_ECUDA; }
     if (getenv("NBGPU_CTAS_PER_SM")) per_sm = std::min(per_sm, atoi(getenv("NBGPU_CTAS_PER_SM")));
     c->per_sm = per_sm;
@@ -1218,23 +1313,26 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     if (c->grid > groups) c->grid = groups;
     c->nslots = c->grid * k.F;
 
-    CK(c, cudaMalloc((void **)&c->d_app, (size_t)c->nslots * N * q * sizeof(float)));
-    CK(c, cudaMalloc((void **)&c->d_ctov, (p->ecn_kind == 1 ? 0 : (size_t)c->nslots * E * k.rec_stride) + 512));
-    if (p->ecn_kind == 1) CK(c, cudaMalloc((void **)&c->d_ctov_dense, (size_t)c->nslots * E * q * sizeof(float)));
-    CK(c, cudaMalloc((void **)&c->d_dec, (size_t)c->nslots * N));
-    CK(c, cudaMemset(c->d_dec, 0, (size_t)c->nslots * N));
-    CK(c, cudaMalloc((void **)&c->d_decide, (size_t)max_batch * N * sizeof(int)));
-    CK(c, cudaMalloc((void **)&c->d_synd, (size_t)max_batch * sizeof(int)));
-    CK(c, cudaMalloc((void **)&c->d_iters, (size_t)max_batch * sizeof(int)));
-    CK(c, cudaMalloc((void **)&c->d_frame_slot, (size_t)max_batch * sizeof(int)));
-    CK(c, cudaMalloc((void **)&c->d_slot_frame, (size_t)c->nslots * sizeof(int)));
-    CK(c, cudaMemset(c->d_slot_frame, 0xff, (size_t)c->nslots * sizeof(int)));
-    CK(c, cudaMalloc((void **)&c->d_queue, 8 * sizeof(unsigned)));       /* [0..3] work queues of up to 4 chunks, [4] slow-path counter */
+    CKF(cudaMalloc((void **)&c->d_app, (size_t)c->nslots * N * q * sizeof(float)));
+    CKF(cudaMalloc((void **)&c->d_ctov, (p->ecn_kind == 1 ? 0 : (size_t)c->nslots * E * k.rec_stride) + 512));
+    if (p->ecn_kind == 1) CKF(cudaMalloc((void **)&c->d_ctov_dense, (size_t)c->nslots * E * q * sizeof(float)));
+    CKF(cudaMalloc((void **)&c->d_dec, (size_t)c->nslots * N));
+    CKF(cudaMemset(c->d_dec, 0, (size_t)c->nslots * N));
+    CKF(cudaMalloc((void **)&c->d_decide, (size_t)max_batch * N * sizeof(int)));
+    CKF(cudaMalloc((void **)&c->d_synd, (size_t)max_batch * sizeof(int)));
+    CKF(cudaMalloc((void **)&c->d_iters, (size_t)max_batch * sizeof(int)));
+    CKF(cudaMalloc((void **)&c->d_frame_slot, (size_t)max_batch * sizeof(int)));
+    CKF(cudaMalloc((void **)&c->d_slot_frame, (size_t)c->nslots * sizeof(int)));
+    CKF(cudaMemset(c->d_slot_frame, 0xff, (size_t)c->nslots * sizeof(int)));
+    CKF(cudaMalloc((void **)&c->d_queue, 8 * sizeof(unsigned)));       /* [0..3] work queues of up to 4 chunks, [4] slow-path counter */
     c->d_slow = c->d_queue + 4;
-    CK(c, cudaMemset(c->d_queue, 0, 8 * sizeof(unsigned)));
+    CKF(cudaMemset(c->d_queue, 0, 8 * sizeof(unsigned)));
     k.app = c->d_app; k.ctov = c->d_ctov; k.dec = c->d_dec; k.ctov_dense = c->d_ctov_dense;
     k.out_decide = c->d_decide; k.out_synd = c->d_synd; k.out_iters = c->d_iters;
     k.frame_slot = c->d_frame_slot; k.slot_frame = c->d_slot_frame; k.queue = c->d_queue; k.slow_counter = c->d_slow;
+    /* the memsets above ran on the legacy stream, the kernels run on c->stream (non-blocking): order them once, here */
+    CKF(cudaDeviceSynchronize());
+#undef CKF
     *out = c;
     return NBGPU_OK;
 }
@@ -1247,10 +1345,7 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
                      c->d_rotout, c->d_img, c->d_inv, c->d_app, c->d_ctov, c->d_dec, c->d_in, c->d_decide, c->d_synd,
                      c->d_iters, c->d_frame_slot, c->d_slot_frame, c->d_queue };
     for (void *b : bufs) if (b) cudaFree(b);
-    void *sbufs[] = { c->src.d_level_ptr, c->src.d_row_order, c->src.d_ut_ptr, c->src.d_ut_col, c->src.d_perm, c->src.d_bit_errors, c->src.d_ut_val,
-                      c->src.d_piv, c->src.d_mulimg, c->src.d_divimg, c->src.d_cw, c->src.d_flag_count, c->src.d_flags, c->src.d_patch_idx,
-                      c->src.d_patch_val };
-    for (void *b : sbufs) if (b) cudaFree(b);
+    source_teardown(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -1280,7 +1375,7 @@ static int upload_common(nbgpu_ctx *c, const float *src, size_t per_frame, int B
     int rc = ensure_input(c, per_frame * (size_t)B);          /* grows on demand: dense-LLR batches are q/log2(q) times larger */
     if (rc) return rc;
     CK(c, cudaMemcpyAsync(c->d_in, src, per_frame * B * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    c->resident_B = B; c->resident_kind = kind;
+    c->resident_B = B; c->resident_kind = kind; c->src.state = 0;
     return NBGPU_OK;
 }
 
@@ -1313,6 +1408,7 @@ extern "C" int nbgpu_run(nbgpu_ctx *c)
     CK(c, cudaGetLastError());
     CK(c, cudaEventRecord(c->ev1, c->stream));
     c->launches += 1;
+    if (c->src.state == 1) c->src.state = 2;
     return NBGPU_OK;
 }
 
@@ -1408,7 +1504,7 @@ static int decode_host(nbgpu_ctx *c, const float *src, size_t per_frame, int kin
     CK(c, cudaSetDevice(c->device));
     int rc = ensure_input(c, per_frame * (size_t)B);
     if (rc) return rc;
-    c->resident_B = B; c->resident_kind = kind;
+    c->resident_B = B; c->resident_kind = kind; c->src.state = 0;
     int lo[5];
     for (int i = 0; i <= nch; i++) lo[i] = (int)(((long)B * i / nch) / c->k.F * c->k.F);
     lo[nch] = B;
@@ -1461,6 +1557,26 @@ extern "C" int nbgpu_decode_llr(nbgpu_ctx *c, const float *llr, int B, int *deci
  * ---------------------------------------------------------------------------------------------- */
 #define SRC_FLAG_CAP (1u << 20)
 
+static uint64_t code_hash(const nbgpu_code *code)
+{
+    uint64_t h = 1469598103934665603ull;                       /* FNV-1a over sizes, graph and coefficients */
+    auto mix = [&h](uint64_t x) { h = (h ^ x) * 1099511628211ull; };
+    mix(code->N); mix(code->M); mix(code->q); mix(code->E);
+    for (int e = 0; e < code->E; e++) mix(((uint64_t)code->col[e] << 16) ^ (uint64_t)code->val[e]);
+    for (int m = 0; m <= code->M; m++) mix(code->row_ptr[m]);
+    return h;
+}
+static void source_teardown(nbgpu_ctx *c)
+{
+    void *sbufs[] = { c->src.d_level_ptr, c->src.d_row_order, c->src.d_ut_ptr, c->src.d_ut_col, c->src.d_perm, c->src.d_bit_errors, c->src.d_ut_val,
+                      c->src.d_piv, c->src.d_mulimg, c->src.d_divimg, c->src.d_cw, c->src.d_flag_count, c->src.d_flags, c->src.d_patch_idx,
+                      c->src.d_patch_val };
+    for (void *b : sbufs) if (b) cudaFree(b);
+    const double margin = c->src.margin;
+    memset(&c->src, 0, sizeof c->src);
+    c->src.margin = margin;
+}
+
 static int source_setup(nbgpu_ctx *c, nbgpu_code *code)
 {
     if (code->N != c->N || code->M != c->M || code->q != c->q) { ctx_err(c, "nbgpu_source_frames: the code is not the one the decoder was created for"); return NBGPU_EINVAL; }
@@ -1507,6 +1623,7 @@ static int source_setup(nbgpu_ctx *c, nbgpu_code *code)
     c->src.nlevels = depth;
     c->src.D = (uint64_t)(code->K + 2 * N) * c->logq;
     if (c->src.margin == 0.0) c->src.margin = 0x1p-46;
+    c->src.code_hash = code_hash(code);
     c->src.ready = 1;
     return NBGPU_OK;
 }
@@ -1539,7 +1656,10 @@ extern "C" int nbgpu_source_frames(nbgpu_ctx *c, nbgpu_code *code, const nbgpu_r
     if ((double)B * c->N * c->logq >= 2147483648.0) { ctx_err(c, "frame source: B*N*log2(q) must stay below 2^31"); return NBGPU_EINVAL; }
     CK(c, cudaSetDevice(c->device));
     int rc;
-    if (!c->src.ready && (rc = source_setup(c, code))) return rc;
+    /* the encoder tables belong to ONE code: another code of the same size gets its own (the stale tables would encode
+     * words of the first code and score the decoder against them) */
+    if (c->src.ready && c->src.code_hash != code_hash(code)) { CK(c, cudaStreamSynchronize(c->stream)); source_teardown(c); }
+    if (!c->src.ready && (rc = source_setup(c, code))) { source_teardown(c); return rc; }
     if ((rc = ensure_input(c, (size_t)c->N * c->logq * B))) return rc;
     const float sigma = nbgpu_sigma(code, EbN);
     nbgpu_rng r = *origin;
@@ -1578,7 +1698,7 @@ extern "C" int nbgpu_source_frames(nbgpu_ctx *c, nbgpu_code *code, const nbgpu_r
         c->launches += 1;
     }
     c->k.den = 2.0 * (double)(float)(sigma * sigma);            /* 2.0*SQR(sigma), channel.c:73 */
-    c->resident_B = B; c->resident_kind = 0; c->src.B = B;
+    c->resident_B = B; c->resident_kind = 0; c->src.B = B; c->src.state = 1;
     return NBGPU_OK;
 }
 
@@ -1605,6 +1725,7 @@ extern "C" int nbgpu_source_download(nbgpu_ctx *c, int *codeword, float *noisy)
 extern "C" int nbgpu_source_results(nbgpu_ctx *c, int *bit_errors, int *synd, int *iters)
 {
     if (!c || !c->src.ready || c->src.B < 1 || c->resident_B != c->src.B) { ctx_err(c, "nbgpu_source_results: no generated batch"); return NBGPU_EINVAL; }
+    if (c->src.state != 2) { ctx_err(c, "nbgpu_source_results: the generated batch %s", c->src.state == 1 ? "has not been decoded (call nbgpu_run)" : "was replaced by an uploaded batch"); return NBGPU_ESTATE; }
     CK(c, cudaSetDevice(c->device));
     const int B = c->src.B;
     SrcArgs a = source_args(c, NULL, B);
@@ -1647,7 +1768,9 @@ extern "C" int nbgpu_get_state(nbgpu_ctx *c, int frame, float *APP, float *CtoV)
     return NBGPU_OK;
 }
 
-/* ---- unit boundaries ---- */
+/* ---- unit boundaries ----
+ * Inputs go to the device with cudaMemcpyAsync on the context's stream (it is a non-blocking stream: work on the legacy
+ * stream is not ordered against it); results come back after cudaStreamSynchronize. */
 template <typename T> struct DevBuf {
     T *p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -1700,13 +1823,12 @@ extern "C" int nbgpu_elementary_step(nbgpu_ctx *c, const float *in1, const float
     CK(c, d1.alloc((size_t)B * n_m)); CK(c, d2.alloc((size_t)B * n_m)); CK(c, dout.alloc((size_t)B * n_m));
     CK(c, ds1.alloc((size_t)B * n_m)); CK(c, ds2.alloc((size_t)B * n_m)); CK(c, dso.alloc((size_t)B * n_m));
     CK(c, dl1.alloc(B)); CK(c, dl2.alloc(B)); CK(c, dlo.alloc(B));
-    CK(c, cudaMemcpy(d1.p, in1, (size_t)B * n_m * 4, cudaMemcpyHostToDevice));
-    CK(c, cudaMemcpy(d2.p, in2, (size_t)B * n_m * 4, cudaMemcpyHostToDevice));
-    CK(c, cudaMemcpy(ds1.p, s1.data(), (size_t)B * n_m, cudaMemcpyHostToDevice));
-    CK(c, cudaMemcpy(ds2.p, s2.data(), (size_t)B * n_m, cudaMemcpyHostToDevice));
-    CK(c, cudaMemcpy(dl1.p, l1.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
-    CK(c, cudaMemcpy(dl2.p, l2.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
-    CK(c, cudaMemset(dso.p, 0, (size_t)B * n_m));
+    CK(c, cudaMemcpyAsync(d1.p, in1, (size_t)B * n_m * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(d2.p, in2, (size_t)B * n_m * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(ds1.p, s1.data(), (size_t)B * n_m, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(ds2.p, s2.data(), (size_t)B * n_m, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(dl1.p, l1.data(), (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(dl2.p, l2.data(), (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
     const int esg = (B + ES_NT - 1) / ES_NT;
     if (q == 16) es_kernel<16><<<esg, ES_NT, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, B, n_m, c->p.nb_oper);
     else if (q == 64) es_kernel<64><<<esg, ES_NT, 0, c->stream>>>(d1.p, d2.p, ds1.p, ds2.p, dl1.p, dl2.p, dout.p, dso.p, dlo.p, B, n_m, c->p.nb_oper);
@@ -1731,8 +1853,8 @@ extern "C" int nbgpu_check_node(nbgpu_ctx *c, int node, const float *vllr, const
     DevBuf<float> dvl, dcl; DevBuf<int> dvg, dcg;
     CK(c, dvl.alloc((size_t)B * dc * n_m)); CK(c, dvg.alloc((size_t)B * dc * n_m));
     CK(c, dcl.alloc((size_t)B * dc * q)); CK(c, dcg.alloc((size_t)B * dc * q));
-    CK(c, cudaMemcpy(dvl.p, vllr, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
-    CK(c, cudaMemcpy(dvg.p, vgf, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpyAsync(dvl.p, vllr, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(dvg.p, vgf, (size_t)B * dc * n_m * 4, cudaMemcpyHostToDevice, c->stream));
     const int grid = c->k.ecn == 1 ? std::min((B + c->k.nw - 1) / c->k.nw, 148) : std::min((B + c->k.cap - 1) / c->k.cap, 148);
     {
         const float *a1 = dvl.p; const int *a2 = dvg.p; float *a3 = dcl.p; int *a4 = dcg.p;
@@ -1754,7 +1876,7 @@ extern "C" int nbgpu_decision_syndrome(nbgpu_ctx *c, const float *app, int *deci
     const int N = c->N, q = c->q;
     DevBuf<float> dapp; DevBuf<int> ddec, dsyn;
     CK(c, dapp.alloc((size_t)B * N * q)); CK(c, ddec.alloc((size_t)B * N)); CK(c, dsyn.alloc(B));
-    CK(c, cudaMemcpy(dapp.p, app, (size_t)B * N * q * 4, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpyAsync(dapp.p, app, (size_t)B * N * q * 4, cudaMemcpyHostToDevice, c->stream));
     const int grid = (int)std::min<long>(((long)B * N + UNIT_NT / 32 - 1) / (UNIT_NT / 32), 148 * 8);
     if (q == 16) decision_kernel<16><<<grid, UNIT_NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
     else if (q == 64) decision_kernel<64><<<grid, UNIT_NT, 0, c->stream>>>(c->k, dapp.p, ddec.p, B);
@@ -1777,7 +1899,7 @@ extern "C" int nbgpu_channel_awgn_bpsk(nbgpu_ctx *c, const float *noisy, float s
     DevBuf<float> dn, dl, dil; DevBuf<int> dig;
     CK(c, dn.alloc((size_t)B * N * c->logq)); CK(c, dl.alloc((size_t)B * N * q));
     if (illr) { CK(c, dil.alloc((size_t)B * N * q)); CK(c, dig.alloc((size_t)B * N * q)); }
-    CK(c, cudaMemcpy(dn.p, noisy, (size_t)B * N * c->logq * 4, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpyAsync(dn.p, noisy, (size_t)B * N * c->logq * 4, cudaMemcpyHostToDevice, c->stream));
     KArgs k = c->k;
     k.den = 2.0 * (double)(float)(sigma * sigma);
     const int grid = (int)std::min<long>(((long)B * N + UNIT_NT / 32 - 1) / (UNIT_NT / 32), 148 * 8);

@@ -24,10 +24,22 @@
 #define NB_FULL 0xffffffffu
 #define NB_KEY_INF 0xffffffffu
 
+/* A warp holds one q-vector ("row"); lane L owns VPL slots.  The slot -> symbol map is chosen so that every row move is
+ * one or two 128-bit accesses per lane over CONTIGUOUS 512-byte spans (bank-conflict free in shared memory, four 128-byte
+ * lines per instruction in global memory): for q = 256 slots 0-3 are symbols 4L..4L+3 and slots 4-7 symbols
+ * 128+4L..128+4L+3.  (A lane-major map, symbols 8L..8L+7, costs twice the wavefronts: the round-1 kernel was bound by
+ * exactly that pipe, l1tex data-stage 81 % busy.) */
 template <int Q> struct QTraits {
     static constexpr int VPL = (Q >= 32) ? Q / 32 : 1;      /* values per lane when a warp holds one row */
     static constexpr int LOGQ = (Q == 16) ? 4 : (Q == 64) ? 6 : 8;
-    static constexpr int SCR_WORDS = (VPL + 2) * 32 > Q ? (VPL + 2) * 32 : Q;   /* per-edge scratch, u32 words */
+    static constexpr int KEY_WORDS = (VPL + 1) * 32;        /* selection queue: sorted keys [rank][lane] + one row of +inf */
+    static constexpr int SCR_WORDS = KEY_WORDS > Q ? KEY_WORDS : Q;   /* per-edge scratch that can hold either the queue or a dense row */
+    __device__ __forceinline__ static int sym(int lane, int j)
+    {
+        if constexpr (Q == 256) return ((j & 4) << 5) | (lane << 2) | (j & 3);
+        else if constexpr (Q == 64) return lane * 2 + j;
+        else return lane;
+    }
 };
 
 /* GF(q) helpers shared by every kernel: byte tables in shared memory (+ global fallback tables) */
@@ -75,8 +87,8 @@ __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("s
 template <int Q> __device__ __forceinline__ void load_row(const float *row, int lane, float (&v)[QTraits<Q>::VPL])
 {
     if constexpr (Q == 256) {
-        const float4 a = reinterpret_cast<const float4 *>(row)[lane * 2];
-        const float4 b = reinterpret_cast<const float4 *>(row)[lane * 2 + 1];
+        const float4 a = reinterpret_cast<const float4 *>(row)[lane];
+        const float4 b = reinterpret_cast<const float4 *>(row)[lane + 32];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else if constexpr (Q == 64) {
         const float2 a = reinterpret_cast<const float2 *>(row)[lane];
@@ -88,8 +100,8 @@ template <int Q> __device__ __forceinline__ void load_row(const float *row, int 
 template <int Q> __device__ __forceinline__ void store_row(float *row, int lane, const float (&v)[QTraits<Q>::VPL])
 {
     if constexpr (Q == 256) {
-        reinterpret_cast<float4 *>(row)[lane * 2] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4 *>(row)[lane * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        reinterpret_cast<float4 *>(row)[lane] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(row)[lane + 32] = make_float4(v[4], v[5], v[6], v[7]);
     } else if constexpr (Q == 64) {
         reinterpret_cast<float2 *>(row)[lane] = make_float2(v[0], v[1]);
     } else {
@@ -119,8 +131,8 @@ __device__ __forceinline__ void stg_f4_hint(float4 *p, const float4 &v, uint64_t
 template <int Q> __device__ __forceinline__ void load_row_hint(const float *row, int lane, float (&v)[QTraits<Q>::VPL], uint64_t pol)
 {
     if constexpr (Q == 256) {
-        const float4 a = ldg_f4_hint(reinterpret_cast<const float4 *>(row) + lane * 2, pol);
-        const float4 b = ldg_f4_hint(reinterpret_cast<const float4 *>(row) + lane * 2 + 1, pol);
+        const float4 a = ldg_f4_hint(reinterpret_cast<const float4 *>(row) + lane, pol);
+        const float4 b = ldg_f4_hint(reinterpret_cast<const float4 *>(row) + lane + 32, pol);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
         load_row<Q>(row, lane, v);
@@ -129,8 +141,8 @@ template <int Q> __device__ __forceinline__ void load_row_hint(const float *row,
 template <int Q> __device__ __forceinline__ void store_row_hint(float *row, int lane, const float (&v)[QTraits<Q>::VPL], uint64_t pol)
 {
     if constexpr (Q == 256) {
-        stg_f4_hint(reinterpret_cast<float4 *>(row) + lane * 2, make_float4(v[0], v[1], v[2], v[3]), pol);
-        stg_f4_hint(reinterpret_cast<float4 *>(row) + lane * 2 + 1, make_float4(v[4], v[5], v[6], v[7]), pol);
+        stg_f4_hint(reinterpret_cast<float4 *>(row) + lane, make_float4(v[0], v[1], v[2], v[3]), pol);
+        stg_f4_hint(reinterpret_cast<float4 *>(row) + lane + 32, make_float4(v[4], v[5], v[6], v[7]), pol);
     } else {
         store_row<Q>(row, lane, v);
     }
@@ -138,8 +150,8 @@ template <int Q> __device__ __forceinline__ void store_row_hint(float *row, int 
 template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, float x)
 {
     if constexpr (Q == 256) {                        /* one register, stored as a quad twice: no broadcast moves */
-        const uint32_t a = smem_u32(row) + lane * 32;
-        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+16], {%1, %1, %1, %1};" :: "r"(a), "f"(x) : "memory");
+        const uint32_t a = smem_u32(row) + lane * 16;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+512], {%1, %1, %1, %1};" :: "r"(a), "f"(x) : "memory");
     } else if constexpr (Q == 64) {
         reinterpret_cast<float2 *>(row)[lane] = make_float2(x, x);
     } else {
@@ -181,25 +193,29 @@ __device__ __forceinline__ void store_record(uint8_t *ctov_f, uint32_t ed, const
     if (lane < n_m) { *reinterpret_cast<float *>(rec + rl.llr) = r.llr; rec[rl.sym] = (uint8_t)r.sym; }
     if (lane == 0) *reinterpret_cast<int2 *>(rec + rl.tail) = make_int2(__float_as_int(r.sat), r.stp);
 }
-/* dense values of this lane's symbols; scr = per-edge scratch (>= q floats), free on return */
+/* Dense values of this lane's symbols from a record, through a CLEAN scratch row (every word +inf on entry and again on
+ * return): the explicit pairs are scattered, the row is read back, the touched words are reset.  A word that still holds
+ * +inf is a symbol without explicit pair and takes the constant.  minform: llr <= sat for every explicit pair (offset >= 0,
+ * bubble_decoder.c:264), so the merge is one FMNMX per value; otherwise a compare + select. */
+#define NB_ROW_CLEAN __int_as_float(0x7f800000)
 template <int Q>
-__device__ __forceinline__ void expand_record(const RecView &r, int lane, float *scr, float (&c)[QTraits<Q>::VPL])
+__device__ __forceinline__ void expand_record(const RecView &r, int lane, float *scr, float (&c)[QTraits<Q>::VPL], bool minform)
 {
     constexpr int VPL = QTraits<Q>::VPL;
-    /* shortcut for the empty record of the first pass (stp = 0, warp-uniform).  Only worth it for q = 256: for the smaller
-     * fields the compiler pays for the branch with moves on every call (measured: +2 % on GF(64) without it) */
-    if constexpr (Q > 64) {
-        if (r.stp == 0) {
+    const bool mine = lane < r.stp;
+    if (mine) scr[r.sym] = r.llr;
+    __syncwarp();
+    float x[VPL];
+    load_row<Q>(scr, lane, x);
+    __syncwarp();
+    if (mine) scr[r.sym] = NB_ROW_CLEAN;
+    if (minform) {
 #pragma unroll
-            for (int j = 0; j < VPL; j++) c[j] = r.sat;
-            return;
-        }
+        for (int j = 0; j < VPL; j++) c[j] = fminf(x[j], r.sat);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VPL; j++) c[j] = (x[j] < NB_ROW_CLEAN) ? x[j] : r.sat;
     }
-    fill_row<Q>(scr, lane, r.sat);
-    __syncwarp();
-    if (lane < r.stp) scr[r.sym] = r.llr;
-    __syncwarp();
-    load_row<Q>(scr, lane, c);
     __syncwarp();
 }
 
@@ -238,7 +254,7 @@ __device__ __forceinline__ void warp_lexmin(float &bv, int &bg)
 
 /* Decision for one row held by a warp (tools.c:317-329): argmin with strict '<' from 1e5, ties ->
  * lowest symbol, default 0.  For non-negative finite rows (the normal case) the float bit pattern is
- * monotone, so one integer REDUX finds the minimum and a ballot the lowest lane holding it. */
+ * monotone: one integer REDUX finds the minimum value, a second one the lowest symbol that holds it. */
 template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTraits<Q>::VPL], int lane)
 {
     constexpr int VPL = QTraits<Q>::VPL;
@@ -250,16 +266,15 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
     if (!__any_sync(NB_FULL, ob >= 0x7f800000u)) {
         const uint32_t m = __reduce_min_sync(NB_FULL, mb);
         if (!(__uint_as_float(m) < NB_SENT)) return 0;
-        const unsigned who = __ballot_sync(NB_FULL, mb == m);
-        int j0 = VPL - 1;
+        uint32_t best = 0xffffu;
 #pragma unroll
-        for (int j = VPL - 2; j >= 0; j--) if (__float_as_uint(v[j]) == m) j0 = j;
-        const int src = __ffs(who) - 1;
-        return src * VPL + __shfl_sync(NB_FULL, j0, src);
+        for (int j = VPL - 1; j >= 0; j--) if (__float_as_uint(v[j]) == m) best = (uint32_t)QTraits<Q>::sym(lane, j);   /* slots ascend in symbol */
+        if (!active) best = 0xffffu;
+        return (int)__reduce_min_sync(NB_FULL, best);
     }
     float bv = NB_SENT; int bg = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < VPL; j++) if (active && v[j] < bv) { bv = v[j]; bg = lane * VPL + j; }
+    for (int j = 0; j < VPL; j++) if (active && v[j] < bv) { bv = v[j]; bg = QTraits<Q>::sym(lane, j); }   /* strict '<' + ascending slots: lowest symbol of the lane */
     warp_lexmin(bv, bg);
     return (bg == 0x7fffffff) ? 0 : bg;
 }
@@ -274,9 +289,12 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
  * when two values differ only in the log2(q) dropped mantissa bits.  Each lane sorts its VPL keys with
  * a register network and parks them in shared memory ([rank][lane], row VPL = +inf); n_m+1 rounds of
  * one REDUX.MIN over the lane heads pop the global minimum, the owning lane stepping to its next row;
- * every lane then re-reads its head row, so the load needs no predicate and no copy
- * (5 instructions per round: redux, setp, predicated st/add, ld).  The NE independent REDUX chains are
- * interleaved so that their latencies overlap.  A result is accepted only if (a) no value was
+ * every lane then re-reads its head row, so the load needs no predicate and no copy.  The minimum comes
+ * back warp-uniform, so lane r simply keeps the result of round r (NB_SEL_CAPTURE = 1: one compare + select, no
+ * shared-memory traffic) or the winner stores it to sel[r] (NB_SEL_CAPTURE = 0).  The NE independent
+ * REDUX chains are interleaved so that their latencies overlap.  The dropped low bits of the winners come
+ * from the owning lane by two shuffles (each lane keeps the low bytes of its VPL values packed in one or two
+ * registers), so no dense row is written for the read-back.  A result is accepted only if (a) no value was
  * negative/NaN/Inf, (b) adjacent winners (including the (n_m+1)-th) differ in their kept bits, (c) the
  * n_m winners are < 1e5.  If only (b) fails and not at the n_m boundary, the winners are re-ordered in
  * place with full comparisons; otherwise that edge re-runs the exact scan (same semantics as the
@@ -285,6 +303,9 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
  * scr[e]: SCR_WORDS u32 of warp-private scratch (free on entry, free on return); sel[e]: 36 u32.
  * Result: lane k < n_m holds (out_llr[e], out_sym[e]) = k-th entry of edge e.
  */
+#ifndef NB_SEL_CAPTURE
+#define NB_SEL_CAPTURE 1
+#endif
 template <int Q, int NE>
 __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::VPL], int lane, uint32_t *(&scr)[NE],
                                              uint32_t *(&sel)[NE], int n_m, float (&out_llr)[NE], int (&out_sym)[NE],
@@ -294,15 +315,30 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
     constexpr int LOGQ = QTraits<Q>::LOGQ;
     const bool active = (Q >= 32) || lane < Q;
     const int rounds = (n_m + 1 < Q) ? n_m + 1 : Q;
-    uint32_t head[NE], nxt[NE], selp[NE];
+    uint32_t head[NE], nxt[NE], selp[NE], mine[NE], lo[NE][2];
     bool bad[NE];
 #pragma unroll
     for (int e = 0; e < NE; e++) {
         uint32_t key[VPL];
+        if constexpr (Q == 256) {
+            /* key = value bits with the low byte replaced by the symbol: one PRMT per value */
+            const uint32_t symA = 0x03020100u + 0x04040404u * (uint32_t)lane, symB = symA | 0x80808080u;
+            uint32_t b[VPL];
 #pragma unroll
-        for (int j = 0; j < VPL; j++) {
-            const uint32_t b = __float_as_uint(mvc[e][j]);
-            key[j] = active ? ((b & ~uint32_t(Q - 1)) | uint32_t(lane * VPL + j)) : NB_KEY_INF;
+            for (int j = 0; j < VPL; j++) b[j] = __float_as_uint(mvc[e][j]);
+#pragma unroll
+            for (int j = 0; j < VPL; j++) key[j] = __byte_perm(b[j], j < 4 ? symA : symB, 0x3214 + (j & 3));
+            lo[e][0] = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+            lo[e][1] = __byte_perm(__byte_perm(b[4], b[5], 0x0040), __byte_perm(b[6], b[7], 0x0040), 0x5410);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VPL; j++) {
+                const uint32_t b = __float_as_uint(mvc[e][j]);
+                key[j] = active ? ((b & ~uint32_t(Q - 1)) | uint32_t(QTraits<Q>::sym(lane, j))) : NB_KEY_INF;
+            }
+            if constexpr (Q == 64) lo[e][0] = (__float_as_uint(mvc[e][0]) & 63u) | ((__float_as_uint(mvc[e][1]) & 63u) << 8);
+            else lo[e][0] = 0;
+            lo[e][1] = 0;
         }
         sort_keys<VPL>(key);
         bad[e] = active && key[VPL - 1] >= 0x7f800000u;
@@ -312,6 +348,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         head[e] = key[0];
         nxt[e] = smem_u32(scr[e] + lane);              /* row of the lane's current head */
         selp[e] = smem_u32(sel[e]);
+        mine[e] = NB_KEY_INF;
     }
     if constexpr (Q == 16 && NE == 2) {
         /* GF(16): a row is one key per lane of a half warp.  Both edges are sorted at once, edge 0 in lanes 0-15 and edge 1 in
@@ -328,9 +365,42 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                 x = (lower == up) ? min(x, y) : max(x, y);
             }
         }
-        (lane < 16 ? sel[0] : sel[1])[lane & 15] = x;
+        mine[0] = __shfl_sync(NB_FULL, x, lane & 15);
+        mine[1] = __shfl_sync(NB_FULL, x, 16 | (lane & 15));
     } else {
     /* no __syncwarp needed: every lane only reads back what it wrote itself */
+#if NB_SEL_CAPTURE
+#define NB_SEL_ROUND(E, OFF)                                                                                   \
+    asm volatile("{\n\t"                                                                                        \
+                 ".reg .pred p, c;\n\t"                                                                         \
+                 ".reg .u32 m;\n\t"                                                                             \
+                 "redux.sync.min.u32 m, %0, 0xffffffff;\n\t"                                                    \
+                 "setp.eq.u32 p, %0, m;\n\t"                                                                    \
+                 "@p add.u32 %1, %1, 128;\n\t"                                                                  \
+                 "ld.shared.u32 %0, [%1];\n\t"                                                                  \
+                 "setp.eq.u32 c, %3, " #OFF ";\n\t"                                                             \
+                 "selp.u32 %2, m, %2, c;\n\t"                                                                   \
+                 "}"                                                                                             \
+                 : "+r"(head[E]), "+r"(nxt[E]), "+r"(mine[E]) : "r"(lr) : "memory")
+    int r = 0;
+    int lr = lane;                                    /* lane - r: lane r keeps the minimum of round r */
+#pragma unroll 1
+    for (; r + 3 <= rounds; r += 3) {                 /* n_m + 1 = 21 rounds for the usual n_m = 20: no remainder */
+#pragma unroll
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
+#pragma unroll
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 1);
+#pragma unroll
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 2);
+        lr -= 3;
+    }
+#pragma unroll 1
+    for (; r < rounds; r++) {
+#pragma unroll
+        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
+        lr -= 1;
+    }
+#else
 #define NB_SEL_ROUND(E, OFF)                                                                                   \
     asm volatile("{\n\t"                                                                                        \
                  ".reg .pred p;\n\t"                                                                            \
@@ -343,7 +413,8 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                  "}"                                                                                             \
                  : "+r"(head[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
     int r = 0;
-    for (; r + 3 <= rounds; r += 3) {                 /* n_m + 1 = 21 rounds for the usual n_m = 20: no remainder */
+#pragma unroll 1
+    for (; r + 3 <= rounds; r += 3) {
 #pragma unroll
         for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
 #pragma unroll
@@ -353,22 +424,36 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
 #pragma unroll
         for (int e = 0; e < NE; e++) selp[e] += 12;
     }
+#pragma unroll 1
     for (; r < rounds; r++) {
 #pragma unroll
         for (int e = 0; e < NE; e++) { NB_SEL_ROUND(e, 0); selp[e] += 4; }
     }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < NE; e++) mine[e] = sel[e][min(lane, rounds - 1)];
+#endif
     }
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < NE; e++) store_row<Q>(reinterpret_cast<float *>(scr[e]), lane, mvc[e]);
-    __syncwarp();
-#pragma unroll
     for (int e = 0; e < NE; e++) {
-        const uint32_t mine = sel[e][min(lane, rounds - 1)];
-        const uint32_t after = sel[e][min(lane + 1, rounds - 1)];
-        const bool amb = lane < n_m && lane + 1 < rounds && ((mine >> LOGQ) == (after >> LOGQ));
-        int sym = int(mine & uint32_t(Q - 1));
-        float val = reinterpret_cast<const float *>(scr[e])[sym];
+        /* lane k: k-th winner; lanes >= rounds hold a copy of the last one (or +inf), which no test below looks at */
+        const uint32_t after = __shfl_down_sync(NB_FULL, mine[e], 1);
+        const bool amb = lane < n_m && lane + 1 < rounds && ((mine[e] >> LOGQ) == (after >> LOGQ));
+        int sym = int(mine[e] & uint32_t(Q - 1));
+        /* the exact value: kept bits from the key, dropped bits from the lane that owns the symbol */
+        uint32_t vb;
+        if constexpr (Q == 256) {
+            const int owner = (sym >> 2) & 31;
+            const uint32_t wa = __shfl_sync(NB_FULL, lo[e][0], owner), wb = __shfl_sync(NB_FULL, lo[e][1], owner);
+            vb = __byte_perm(mine[e], __byte_perm(wa, wb, (uint32_t)((sym & 3) | ((sym >> 5) & 4))), 0x3214);
+        } else if constexpr (Q == 64) {
+            const uint32_t w = __shfl_sync(NB_FULL, lo[e][0], sym >> 1);
+            vb = (mine[e] & ~63u) | ((w >> (8 * (sym & 1))) & 63u);
+        } else {
+            vb = __float_as_uint(__shfl_sync(NB_FULL, mvc[e][0], sym));
+        }
+        float val = __uint_as_float(vb);
         const bool over = lane < n_m && !(val < NB_SENT);
         if (__any_sync(NB_FULL, bad[e] || amb || over)) {                      /* rare: one vote on the common path */
         const unsigned ambs = __ballot_sync(NB_FULL, amb);
@@ -392,7 +477,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                 }
             } while (__any_sync(NB_FULL, moved));
         } else {
-            /* exact scan, NB_LDPC.c:356-369 */
+            /* exact scan, NB_LDPC.c:356-369.  Inside a lane the slots ascend in symbol, so strict '<' keeps the lowest */
             if (slow_counter && lane == 0) atomicAdd(slow_counter, 1u);
             float tmp[VPL];
 #pragma unroll
@@ -400,11 +485,11 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
             for (int k = 0; k < n_m; k++) {
                 float bv = NB_SENT; int bg = 0x7fffffff;
 #pragma unroll
-                for (int j = 0; j < VPL; j++) if (active && tmp[j] < bv) { bv = tmp[j]; bg = lane * VPL + j; }
+                for (int j = 0; j < VPL; j++) if (active && tmp[j] < bv) { bv = tmp[j]; bg = QTraits<Q>::sym(lane, j); }
                 warp_lexmin(bv, bg);
                 if (bg == 0x7fffffff) bg = 0;                      /* nothing below 1e5: (1e5, symbol 0) */
 #pragma unroll
-                for (int j = 0; j < VPL; j++) if (bg == lane * VPL + j) tmp[j] = NB_SENT;   /* NB_LDPC.c:368 */
+                for (int j = 0; j < VPL; j++) if (active && bg == QTraits<Q>::sym(lane, j)) tmp[j] = NB_SENT;   /* NB_LDPC.c:368 */
                 if (lane == k) { val = bv; sym = bg; }
             }
         }

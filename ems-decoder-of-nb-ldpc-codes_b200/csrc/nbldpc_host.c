@@ -259,13 +259,17 @@ fail:
 int nbgpu_code_from_arrays(nbgpu_code **out, int N, int M, int q, const int *row_deg, const int *col,
                            const int *val, const int *bingf, const int *addgf, const int *mulgf, const int *divgf)
 {
+    if (!out) { nbgpu_set_global_error("nbgpu_code_from_arrays: NULL output pointer"); return NBGPU_EINVAL; }
     *out = NULL;
     if (N <= 0 || M <= 0 || M > N || !row_deg || !col || !val) { nbgpu_set_global_error("bad code arrays"); return NBGPU_EINVAL; }
+    /* the kernels exist for the fields the reference's LoadTables knows (init.c:431-435): GF(16), GF(64), GF(256) */
+    if (q != 16 && q != 64 && q != 256) { nbgpu_set_global_error("GF(%d) is not supported (16, 64 or 256)", q); return NBGPU_EINVAL; }
     struct nbgpu_code *c = calloc(1, sizeof *c);
+    if (!c) { nbgpu_set_global_error("out of memory"); return NBGPU_ENOMEM; }
     int rc;
     c->N = N; c->M = M; c->K = N - M; c->q = q;
     c->logq = (int)rint(log((double)q) / log(2.0));
-    if ((1 << c->logq) != q || q < 4 || q > 256 || (!bingf && !field_poly(q))) {
+    if ((1 << c->logq) != q || (!bingf && !field_poly(q))) {
         nbgpu_set_global_error("GF(%d) is not supported", q); free(c); return NBGPU_EINVAL;
     }
     c->rate = (float)(N - M) / N;
