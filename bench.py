@@ -28,9 +28,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)          # the product binding (nbldpc.py); tests/ and oracle/ stay off the product arm's path
 
 # name -> (matrix, n_m, nb_oper, offset, Eb/N0, default frames per GPU per step)        
 WORKLOADS = {
@@ -43,6 +42,8 @@ WORKLOADS = {
     "KN_64800_R34_GF256": ("matrices/KN/N64800_K48600_GF256.txt", 20, 25, 0.3, 3.4, 2368),
 }
 NO_REFERENCE = {"KN_64800_R34_GF256"}
+# index of the workload in BASELINE.json "configs" (1-based, as SURVEY.md section 8d numbers them)
+BASELINE_CONFIG = {"N96_K48_GF64": 1, "Mat24_N480_M240": 2, "MatDeclercq_R12_GF64": 3, "Ahmed_64800_R34_GF16": 4, "AD_64800_R12_GF256": 5}
 NB_ITER_MAX = 10
 # syndrome_ems parameters (d1, d2, d3, truncation, n_cv): the shapes of the commented call site NB_LDPC.c:185-201 with
 # d1 capped at n_m-1 (its d_1 = 40 overruns the n_m-wide message rows); see DESIGN.md "Syndrome path"
@@ -163,6 +164,7 @@ def run_reference_cpu(wl, frames_per_proc, procs, seconds_hint=None, ecn="bubble
 
 def _port_worker(arg):
     wl, frames, idx, ecn = arg
+    sys.path.insert(0, os.path.join(ROOT, "tests"))          # the oracle port: cpu_baseline fallback only, never the product arm
     import oracle_lib as ol
     matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
     o = ol.Oracle(find_matrix(matrix))
@@ -189,26 +191,46 @@ def cpu_sample_size(wl, ecn="bubble"):
     return max(1, n // 6) if ecn == "syndrome" else n
 
 
+class AlistHeader:
+    """N, M, GF and the check degree read from the matrix file itself: the reference arm must not load the product library."""
+    def __init__(self, path):
+        tok = open(path).read().split()
+        self.N, self.M, self.q = int(tok[0]), int(tok[1]), int(tok[2])
+        self.logq = self.q.bit_length() - 1
+        self.info_bits = (self.N - self.M) * self.logq          # the reference exits when H is rank deficient (tools.c:181-185)
+        self.dc_max = max(int(x) for x in tok[3 + self.N:3 + self.N + self.M])
+        self.dc_min = min(int(x) for x in tok[3 + self.N:3 + self.N + self.M])
+
+
 def reference_arm(args, rank, world):
+    """The reference's own CPU decoder (unmodified main loop) on all host cores; rank 0 only.  --steps/--warmup are honoured:
+    a step is one concurrent batch of `cores` single-thread processes, sized after a calibration run so that the whole
+    arm ends within a few minutes."""
     if rank != 0:
         return
-    import nbldpc
     wl = args.workload
     matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
-    code = nbldpc.Code(find_matrix(matrix))
+    code = AlistHeader(find_matrix(matrix))
     cores = host_cores()
-    fpp = max(1, cpu_sample_size(wl, args.ecn) // 2)
-    for _ in range(min(args.warmup, 1)):
+    budget_s = float(os.environ.get("NBLDPC_REF_BUDGET_S", "240"))
+    # calibration (also the first warm-up step): one frame per process
+    c0 = time.time()
+    run_reference_cpu(wl, 1, cores, ecn=args.ecn)
+    per_frame_s = max(time.time() - c0, 1e-3)
+    warm = max(args.warmup, 1)
+    fpp = int(max(1, min(cpu_sample_size(wl, args.ecn) * 4, (budget_s - warm * per_frame_s) / (args.steps * per_frame_s))))
+    for _ in range(warm - 1):
         run_reference_cpu(wl, 1, cores, ecn=args.ecn)
-    rates, walls = [], []
-    steps = max(1, min(args.steps, 3))
-    for _ in range(steps):
+    rates, walls, frames = [], [], 0
+    for _ in range(args.steps):
         rate, kind, sample, wall, nfr = run_reference_cpu(wl, fpp, cores, ecn=args.ecn)
-        rates.append(rate); walls.append(wall)
+        rates.append(rate); walls.append(wall); frames += nfr
     fps = statistics.mean(rates)
     val = fps * code.info_bits / 1e6
+    sample += "; %d timed steps (%d frames per process in total, %d frames over all cores), %d warm-up steps of 1 frame per process" % (
+        args.steps, fpp * args.steps, frames, warm)
     line = {"impl": "reference", "metric": "decoded info Mbit/s at fixed iterations (%d passes)" % (NB_ITER_MAX - 1), "value": val,
-            "unit": "Mbit/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * statistics.mean(walls),
+            "unit": "Mbit/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(walls),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (reference's own drand48 frame stream)",
             "frames_per_s": fps,
             "config": config_dict(wl, code, fpp * cores, "host CPU only", args.ecn),
@@ -223,11 +245,15 @@ def config_dict(wl, code, frames, note, ecn="bubble"):
         cn = "syndrome-based check node (syndrome_ems with presorting, d=(%d,%d,%d), %d configurations max, n_cv=%d)" % SYND[n_m]
     else:
         cn = "L-Bubble forward/backward EMS check node (CheckPassLogEMS), nbOper=%d" % nb_oper
-    return {"workload": "%s: N=%d symbols over GF(%d) (%d code bits, %d info bits), M=%d, dc=%d, %s, n_m=%d, offset=%.1f, "
+    idx = BASELINE_CONFIG.get(wl)
+    which = "BASELINE.json configs[%d] (config %d of SURVEY.md 8d) = " % (idx - 1, idx) if idx else "extra workload (not in BASELINE.json) = "
+    if idx == 5:
+        which += "as written (syndrome_decoder path) " if ecn == "syndrome" else "with the reference's shipped check node (NB_LDPC.c:392) "
+    return {"workload": which + "%s: N=%d symbols over GF(%d) (%d code bits, %d info bits), M=%d, dc=%d, %s, n_m=%d, offset=%.1f, "
                         "NbIterMax=%d (= %d passes, early termination off), AWGN BPSK Eb/N0=%.1f dB"
                         % (wl, code.N, code.q, code.N * code.logq, code.info_bits, code.M, code.dc_max, cn, n_m, offset, NB_ITER_MAX,
                            NB_ITER_MAX - 1, ebn),
-            "frames_per_step_per_gpu": frames, "cache": note}
+            "baseline_config": idx, "check_node": ecn, "frames_per_step_per_gpu": frames, "cache": note}
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -251,33 +277,45 @@ def synth_frames(code, B, ebn, seed, pool=8):
     return noisy, bits[idx], sigma
 
 
-def ours(args, rank, local_rank, world):
-    import nbldpc
-    dist = None
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout, next to the JSON line
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if nbldpc.device_count() < 1:
-        raise RuntimeError("bench.py needs a B200: the product has no CPU fallback")
-    wl = args.workload
-    matrix, n_m, nb_oper, offset, ebn, dflt_B = WORKLOADS[wl]
-    B = args.frames or (SYND_FRAMES.get(wl, dflt_B) if args.ecn == "syndrome" else dflt_B)
-    code = nbldpc.Code(find_matrix(matrix))
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True).stdout.strip() or None
+    except OSError:
+        return None
+
+
+def measured_traffic(wl, ecn, B, kernel_ms):
+    """DRAM bytes per launch of the decode kernel from an ncu capture (profiles/traffic_<workload>_<ecn>.json, written by
+    scripts/gpu_traffic.sh).  Only a capture of THIS kernel counts: same workload, check node and frames per launch, and a
+    kernel duration within 3 % of the one measured live -- otherwise the figure is stale and null is reported."""
+    tp = os.path.join(ROOT, "profiles", "traffic_%s_%s.json" % (wl, ecn))
+    if not os.path.exists(tp):
+        return None, None
+    tj = json.load(open(tp))
+    if tj.get("frames") != B or tj.get("ecn") != ecn or not tj.get("kernel_ms"):
+        return None, {"capture": os.path.basename(tp), "rejected": "other launch size or check node"}
+    dev = abs(tj["kernel_ms"] - kernel_ms) / kernel_ms
+    info = {"capture": os.path.basename(tp), "git": tj.get("git"), "kernel_ms_at_capture": tj["kernel_ms"], "kernel_ms_deviation": dev}
+    if dev > 0.03:
+        info["rejected"] = "kernel duration differs by more than 3 % from the live measurement: capture is stale"
+        return None, info
+    return tj.get("dram_bytes_per_launch"), info
+
+
+def measure_leg(nbldpc, code, wl, ecn, B, args, rank, local_rank, world, dist, noisy, bits, sigma, out, with_sim):
+    """One check node on one workload: resident-input throughput, end-to-end throughput through the C ABI with host buffers,
+    roofline of the decode kernel, counters.  Same steps / warm-up for every leg."""
+    matrix, n_m, nb_oper, offset, ebn, _ = WORKLOADS[wl]
     passes = NB_ITER_MAX - 1
     kw = {}
-    if args.ecn == "syndrome":
+    if ecn == "syndrome":
         d1, d2, d3, trunc, n_cv = SYND[n_m]
         kw = dict(ecn_kind=1, d1=d1, d2=d2, d3=d3, cfg_trunc=trunc, n_cv=n_cv)
     dec = nbldpc.Decoder(code, n_m, nb_oper, NB_ITER_MAX, offset, early_stop=False, device=local_rank, max_batch=B,
                          frames_per_cta=args.frames_per_cta, cns_per_step=args.cns_per_step, **kw)
     geo = dec.geometry()
-    noisy, bits, sigma = synth_frames(code, B, ebn, rank)
-    nbldpc.pin(noisy)
-    out = (nbldpc.pin(np.zeros((B, code.N), np.int32)), nbldpc.pin(np.zeros(B, np.int32)), nbldpc.pin(np.zeros(B, np.int32)))
+    noisy = noisy[:B]
+    out = tuple(o[:B] for o in out)
 
     def barrier():
         if dist is not None:
@@ -335,7 +373,7 @@ def ours(args, rank, local_rank, world):
 
     # ---------------- whole simulation step on the device: frame source -> decode -> error count ----------------
     sim = None
-    if not args.no_also:
+    if with_sim:
         dec.source_frames(rank * B, B, ebn)
         dec.run(); dec.source_results()
         nsim = min(args.steps, 3)
@@ -352,14 +390,36 @@ def ours(args, rank, local_rank, world):
                "note": "Monte-Carlo step with the frames of the reference's drand48 stream generated, decoded (fixed iterations) and scored on the "
                        "device: nbgpu_source_frames + nbgpu_run + nbgpu_source_results"}
 
-    # ---------------- counters: one NCCL all-reduce (the only collective of the path) ----------------
-    bit_err = int((bits[:, :code.K, :] != np.stack([code_bits(code, d_res[:, k]) for k in range(code.K)], axis=1)).sum()) if args.count_errors else -1
+    # ---------------- counters: one all-reduce (the only collective of the path) ----------------
+    bit_err = int((bits[:B, :code.K, :] != np.stack([code_bits(code, d_res[:, k]) for k in range(code.K)], axis=1)).sum()) if args.count_errors else -1
     counters = np.array([B, int((s_res != 0).sum()), int(it_res.sum()), bit_err], np.int64)
     counters = nbldpc.multigpu.allreduce_counters(counters, device="cuda" if dist is not None else None)
 
-    line = None
+    # ---------------- sharding check (N > 1): frames [0, N*Bc) of the reference's stream generated on the devices, one block per
+    # rank, early termination on; the all-reduced counters must equal those of ONE GPU decoding the same range ----------------
+    shard = None
+    if world > 1 and ecn == "bubble":
+        Bc = min(B, 296)
+        dchk = nbldpc.Decoder(code, n_m, nb_oper, NB_ITER_MAX, offset, early_stop=True, device=local_rank, max_batch=Bc)
+
+        def block(r):
+            dchk.source_frames(r * Bc, Bc, ebn)
+            dchk.run()
+            e, sy, it = dchk.source_results()
+            return np.array([Bc, int((e != 0).sum()), int(((e != 0) & (sy == 0)).sum()), int(e.sum()), int(it.sum())], np.int64)
+
+        mine = nbldpc.multigpu.allreduce_counters(block(rank), device="cuda")
+        if rank == 0:
+            alone = sum(block(r) for r in range(world))
+            shard = {"frames": int(world * Bc), "counters": ["frames", "erroneous_frames", "undetected", "bit_errors", "sum_iterations"],
+                     "all_reduced": [int(x) for x in mine], "single_gpu_same_range": [int(x) for x in alone],
+                     "equal": bool((np.asarray(mine) == alone).all())}
+        dchk.close()
+        barrier()
+
+    leg = None
     if rank == 0:
-        bpf = bytes_per_frame(code.N, code.E, code.q, n_m, passes, args.ecn)
+        bpf = bytes_per_frame(code.N, code.E, code.q, n_m, passes, ecn)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -367,54 +427,84 @@ def ours(args, rank, local_rank, world):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bpf * B / (kernel_ms / 1e3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl)
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            if tj.get("frames") == B and tj.get("ecn", "bubble") == args.ecn:
-                traffic = tj.get("dram_bytes_per_launch")
-        line = {"metric": "decoded info Mbit/s at fixed iterations (%d passes)" % passes, "value": value, "unit": "Mbit/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        traffic, tinfo = measured_traffic(wl, ecn, B, kernel_ms)
+        slot_bytes = code.N * code.q * 4 + code.E * (code.q * 4 if ecn == "syndrome" else (5 * n_m + 8 + 15) // 16 * 16)
+        leg = {"value": value, "unit": "Mbit/s", "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "frames_per_s": fps,
+               "config": config_dict(wl, code, B, "per-step working set %.1f GB and inputs %.0f MB per GPU, both larger than the 126 MB L2 (no explicit flush)"
+                                     % (geo["slots"] * slot_bytes / 1e9, noisy.nbytes / 1e6), ecn),
+               "geometry": geo,
+               "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": int(noisy.nbytes), "d2h_bytes_per_step": int(sum(o.nbytes for o in out)),
+                       "ms_per_step": 1e3 * e2e_s / args.steps},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "traffic_source": tinfo,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                            "kernel": "decode_kernel<%d, closed, %s>" % (code.q, "syndrome_ems" if ecn == "syndrome" else "CheckPassLogEMS"),
+                            "kernel_ms": kernel_ms, "bytes_per_frame": bpf, "frames_per_launch": B},
+               "clocks": clocks, "simulation": sim,
+               "counters": {"frames_per_step": int(counters[0]), "frames_nonzero_syndrome": int(counters[1]), "sum_iterations": int(counters[2]),
+                            "slow_path_selects": dec.slow_selects()}}
+        if shard is not None:
+            leg["sharding_check"] = shard
+    dec.close()
+    return leg
+
+
+def ours(args, rank, local_rank, world):
+    import nbldpc
+    dist = None
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout, next to the JSON line
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if nbldpc.device_count() < 1:
+        raise RuntimeError("bench.py needs a B200: the product has no CPU fallback")
+    wl = args.workload
+    matrix, n_m, nb_oper, offset, ebn, dflt_B = WORKLOADS[wl]
+    code = nbldpc.Code(find_matrix(matrix))
+    synd_ok = n_m in SYND and code.dc_min == code.dc_max and 4 <= code.dc_max <= 8
+    B_of = {"bubble": args.frames or dflt_B, "syndrome": args.frames or SYND_FRAMES.get(wl, dflt_B)}
+    # the headline leg is the check node asked for; the default run carries the other one of the workload as a second, complete leg
+    legs = [args.ecn]
+    if not args.no_also and synd_ok and wl in BASELINE_CONFIG:
+        legs.append("syndrome" if args.ecn == "bubble" else "bubble")
+    Bmax = max(B_of[e] for e in legs)
+    noisy, bits, sigma = synth_frames(code, Bmax, ebn, rank)
+    nbldpc.pin(noisy)
+    out = (nbldpc.pin(np.zeros((Bmax, code.N), np.int32)), nbldpc.pin(np.zeros(Bmax, np.int32)), nbldpc.pin(np.zeros(Bmax, np.int32)))
+    res = {}
+    for i, ecn in enumerate(legs):
+        res[ecn] = measure_leg(nbldpc, code, wl, ecn, B_of[ecn], args, rank, local_rank, world, dist, noisy, bits, sigma, out, with_sim=(i == 0 and not args.no_also))
+    if rank == 0:
+        passes = NB_ITER_MAX - 1
+        head = res[legs[0]]
+        line = {"metric": "decoded info Mbit/s at fixed iterations (%d passes)" % passes, "value": head["value"], "unit": "Mbit/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (encoder codewords + numpy Gaussian noise at the reference's sigma)",
-                "frames_per_s": fps,
-                "config": config_dict(wl, code, B, "per-step working set %.1f GB and inputs %.0f MB per GPU, both larger than the 126 MB L2 (no explicit flush)"
-                                      % (geo["slots"] * (code.N * code.q * 4 + code.E * (code.q * 4 if args.ecn == "syndrome" else (5 * n_m + 8 + 15) // 16 * 16)) / 1e9, noisy.nbytes / 1e6), args.ecn),
-                "geometry": geo,
-                "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": int(noisy.nbytes), "d2h_bytes_per_step": int(sum(o.nbytes for o in out)),
-                        "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                             "kernel": "decode_kernel<%d, closed, %s>" % (code.q, "syndrome_ems" if args.ecn == "syndrome" else "CheckPassLogEMS"), "kernel_ms": kernel_ms, "bytes_per_frame": bpf, "frames_per_launch": B},
-                "clocks": clocks, "simulation": sim,
-                "counters": {"frames_per_step": int(counters[0]), "frames_nonzero_syndrome": int(counters[1]), "sum_iterations": int(counters[2]),
-                             "slow_path_selects": dec.slow_selects()}}
-        if world == 1 and args.ecn == "bubble" and not args.no_also and n_m in SYND and code.dc_min == code.dc_max and 4 <= code.dc_max <= 8:
-            # the same frames through the reference's other check node (syndrome_ems): a short extra leg, not the headline
-            dec.close()
-            Bs = min(B, args.frames or SYND_FRAMES.get(wl, B))
-            d1, d2, d3, trunc, n_cv = SYND[n_m]
-            ds = nbldpc.Decoder(code, n_m, nb_oper, NB_ITER_MAX, offset, early_stop=False, device=local_rank, max_batch=Bs,
-                                ecn_kind=1, d1=d1, d2=d2, d3=d3, cfg_trunc=trunc, n_cv=n_cv)
-            ds.upload_noisy(noisy[:Bs], sigma)
-            ds.run(); ds.sync()
-            ds.timer_begin()
-            ds.run(); ds.run()
-            sms = ds.timer_end() / 2
-            line["also"] = {"check_node": "syndrome_ems d=(%d,%d,%d), %d configurations max, n_cv=%d" % SYND[n_m], "value": Bs / (sms / 1e3) * code.info_bits / 1e6,
-                            "unit": "Mbit/s", "frames_per_step": Bs, "ms_per_step": sms, "steps": 2, "warmup": 1,
-                            "note": "same workload with NB_LDPC.c:388 instead of :392 as check node; run `bench.py --ecn syndrome` for its full line"}
-            ds.close()
+                "git": git_head()}
+        for k in ("frames_per_s", "config", "geometry", "e2e", "gpu_launches", "roofline", "clocks", "simulation", "counters", "sharding_check"):
+            if k in head:
+                line[k] = head[k]
         if world == 1 and not args.no_cpu and wl not in NO_REFERENCE:
             cores = host_cores()
-            rate, kind, sample, wall, nfr = run_reference_cpu(wl, cpu_sample_size(wl, args.ecn), cores, ecn=args.ecn)
-            line["cpu_baseline"] = {"value": rate * code.info_bits / 1e6, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample,
-                                    "frames_per_s": rate, "wall_s": wall}
+            for ecn in legs:
+                rate, kind, sample, wall, nfr = run_reference_cpu(wl, cpu_sample_size(wl, ecn), cores, ecn=ecn)
+                res[ecn]["cpu_baseline"] = {"value": rate * code.info_bits / 1e6, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample,
+                                            "frames_per_s": rate, "wall_s": wall}
+            line["cpu_baseline"] = head["cpu_baseline"]
+        if len(legs) > 1:
+            other = res[legs[1]]
+            other["note"] = "the same workload and frames through the reference's other check node (NB_LDPC.c:%s instead of :%s), measured like the " \
+                            "headline leg (same steps and warm-up); `bench.py --ecn %s` makes it the headline" % (
+                                ("388", "392", "syndrome") if legs[1] == "syndrome" else ("392", "388", "bubble"))
+            line["config5_as_written" if (legs[1] == "syndrome" and BASELINE_CONFIG.get(wl) == 5) else "other_check_node"] = other
         print(json.dumps(line), flush=True)
     nbldpc.unpin(noisy)
     for o in out:
         nbldpc.unpin(o)
-    dec.close()
     if dist is not None:
         dist.destroy_process_group()
 

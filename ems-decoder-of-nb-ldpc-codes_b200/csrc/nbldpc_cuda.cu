@@ -41,12 +41,16 @@
 
 #ifndef NT_MAX
 #define NT_MAX 384
+#endif
+#ifndef NT_SYND
 #define NT_SYND 256              /* syndrome check node: at most 8 warps per CTA (its shared memory allows 7 at 945 configurations), 128 registers */        /* threads per CTA (upper bound; the plan may use fewer warps) */
 #endif
 #ifndef CTAS_PER_SM
 #define CTAS_PER_SM 2      /* resident CTAs per SM the decode kernel is compiled for (register cap 65536 / (NT_MAX * CTAS_PER_SM)) */
 #endif
+#ifndef NE
 #define NE 2              /* edges interleaved per warp in phases 1 and 3 */
+#endif
 #ifndef NB_L2_PREFETCH
 #define NB_L2_PREFETCH 1   /* phase 1 pulls the next pair's APP rows and records into L2 while the current pair is selected */
 #endif
@@ -119,11 +123,18 @@ __device__ __forceinline__ int id_out(int dc, int t)
     return id_M(dc, t - 1);
 }
 
-/* tile description in shared memory: per check node {first edge | degree << 24, frame}; reads come back as int4 {e0, dc, f, 0} */
+/* tile description in shared memory, per check node: {first edge | degree << 24 (0 = skip), byte offset of the frame's APP block,
+ * byte offset of the node's first CtoV record (or dense row), offset of the frame's decisions}, all relative to the CTA's slot block
+ * and computed once per tile by one lane per node (the phases add a variable / edge offset to them: no 64-bit multiplies per edge) */
 struct TileMeta {
-    int2 *p;
-    __device__ __forceinline__ int4 operator[](int c) const { const int2 m = p[c]; return make_int4(m.x & 0xffffff, (int)((unsigned)m.x >> 24), m.y, 0); }
-    __device__ __forceinline__ void set(int c, int e0, int dc, int f) const { p[c] = make_int2(e0 | (dc << 24), f); }
+    int4 *p;
+    __device__ __forceinline__ int4 operator[](int c) const { return p[c]; }
+    __device__ __forceinline__ void set(int c, int e0, int dc, uint32_t app_off, uint32_t rec_off, uint32_t dec_off) const
+    {
+        p[c] = make_int4(e0 | (dc << 24), (int)app_off, (int)rec_off, (int)dec_off);
+    }
+    __device__ __forceinline__ static int e0(const int4 &m) { return m.x & 0xffffff; }
+    __device__ __forceinline__ static int dc(const int4 &m) { return (int)((unsigned)m.x >> 24); }
 };
 
 /* a warp's private shared memory */
@@ -149,7 +160,7 @@ template <int Q> struct WarpMem {
             row3[e] = reinterpret_cast<float *>(wb + a.wb_scr3) + e * Q;
         }
         mask = smem_u32(wa + a.wa_mask);
-        meta.p = reinterpret_cast<int2 *>(wa + a.wa_meta);
+        meta.p = reinterpret_cast<int4 *>(wa + a.wa_meta);
         ew = reinterpret_cast<uint32_t *>(wa + a.wa_einfo);
         ls.base = smem_u32(wb + a.wb_U); ls.lenb = smem_u32(wa + a.wa_len);
         ls.lstride = a.lstride; ls.n_m = a.n_m; ls.dcm = a.dc_max; ls.lr = a.L - a.dc_max; ls.r0 = a.cpw * a.dc_max;
@@ -168,7 +179,7 @@ __device__ __forceinline__ void tile_elementary_steps(const Lists &ls, const Til
         for (int cb = 0; cb < cnt; cb += 8) {
             const int c = cb + (lane >> 2), slot = lane & 3;
             if (c < cnt) {
-                const int dc = meta[c].y;
+                const int dc = TileMeta::dc(meta[c]);
                 int a = 0, b = 0, o = 0;
                 bool valid = false;
                 if (slot == 0) { valid = r <= dc - 2; a = id_F(dc, r - 1); b = r; o = id_F(dc, r); }
@@ -292,7 +303,7 @@ __device__ __forceinline__ void synd_dense_row(uint32_t out, const GFTab &gf, in
     }
 }
 
-/* L2 prefetch of the APP rows and CtoV records of up to NE consecutive edges (one instruction) */
+/* L2 prefetch of the APP rows and CtoV records of up to NE consecutive edges (one instruction) -- GF(16) path */
 template <int Q>
 __device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t *ctov_f, const uint32_t *einfo, int ed, int n,
                                                int rec_stride, int lane)
@@ -307,6 +318,24 @@ __device__ __forceinline__ void prefetch_edges(const float *app_f, const uint8_t
         if (off < n * rec_stride) p = reinterpret_cast<const char *>(ctov_f + (size_t)ed * rec_stride) + off;
     }
     if (p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+/* L2 prefetch of everything phase 1 reads for ONE check node of the tile: its dc APP rows (edge words already in shared memory)
+ * and its dc consecutive records.  Issued one node ahead: two or three instructions per node instead of address arithmetic per
+ * edge pair. */
+template <int Q>
+__device__ __forceinline__ void prefetch_node(const char *app, const char *ctov, const uint32_t *ew, const int4 &m, int rec_stride, int lane)
+{
+    constexpr int LPR = (Q * 4) / 128;                     /* 128-byte lines per row: 8 (q = 256), 2 (q = 64) */
+    const int dc = TileMeta::dc(m);
+    for (int i = lane; i < dc * LPR; i += 32) {
+        const uint32_t ei = ew[i / LPR];
+        const char *p = app + (uint32_t)m.y + (ei & 0xfffffu) * (uint32_t)(Q * 4) + (uint32_t)(i % LPR) * 128u;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
+    if (lane * 128 < dc * rec_stride) {
+        const char *p = ctov + (uint32_t)m.z + (uint32_t)lane * 128u;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -448,12 +477,12 @@ __device__ __forceinline__ void gf16_phase3(const WarpMem<16> &wm, const GFTab &
 
 /* ------------------------------------------------------------------------------------------------
  * Bubble path, q >= 64: phases 1 and 3 of a warp's tile.  Two edges are in flight per warp (NE): their global loads,
- * shared-memory round trips and REDUX chains interleave.
+ * shared-memory round trips and REDUX chains interleave.  app / ctov / dec: the CTA's slot block; the tile meta holds the
+ * byte offsets of every node's frame in it.
  * ---------------------------------------------------------------------------------------------- */
 template <int Q, bool CLOSED>
-__device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm, const GFTab &gf, int cnt, float *app, uint8_t *ctov,
-                                            size_t frame_app, size_t frame_ctov, const RecLane &rl, uint64_t pol_first, uint64_t pol_keep,
-                                            bool minform, int lane)
+__device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm, const GFTab &gf, int cnt, const char *app, const char *ctov,
+                                            const RecLane &rl, uint64_t pol_first, uint64_t pol_keep, bool minform, int lane)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     const Lists &ls = wm.ls;
@@ -463,10 +492,10 @@ __device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm
     __syncwarp();
     for (int c = 0; c < cnt; c++) {
         const int4 mt = wm.meta[c];
-        const int e0 = mt.x, dc = mt.y;
-        float *app_f = app + mt.z * frame_app;
-        const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
-        if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
+        const int dc = TileMeta::dc(mt);
+        if (NB_L2_PREFETCH && c + 1 < cnt) prefetch_node<Q>(app, ctov, wm.ew + (c + 1) * dcm, wm.meta[c + 1], rs, lane);
+        const char *app_f = app + (uint32_t)mt.y;
+        const uint8_t *rec0 = reinterpret_cast<const uint8_t *>(ctov) + (uint32_t)mt.z;      /* record of the node's edge 0 */
         for (int t = 0; t < dc; t += NE) {
             float v[NE][VPL];
             RecView r[NE];
@@ -475,20 +504,12 @@ __device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm
 #pragma unroll
             for (int e = 0; e < NE; e++) {
                 const int te = min(t + e, dc - 1);                 /* t+e >= dc: duplicate of the last edge, result ignored */
-                const uint32_t ed = (uint32_t)(e0 + te);
                 const uint32_t ei = wm.ew[c * dcm + te];
                 hv[e] = (ei >> 20) & 0xff;
-                prow[e] = app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q);
+                prow[e] = reinterpret_cast<float *>(const_cast<char *>(app_f) + (ei & 0xfffffu) * (uint32_t)(Q * 4));
                 /* the row comes back in phase 3 (as the parked Mvc or as itself): keep it in L2 */
                 load_row_hint<Q>(prow[e], lane, v[e], NB_PARK_MVC ? pol_first : pol_keep);
-                r[e] = load_record(ctov_f, ed, rl);
-            }
-            /* next pair of edges of the tile -> L2 while this pair is processed */
-            if (!NB_L2_PREFETCH) { }
-            else if (t + NE < dc) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0 + t + NE, min(NE, dc - t - NE), rs, lane);
-            else if (c + 1 < cnt) {
-                const int4 nx = wm.meta[c + 1];
-                if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
+                r[e] = load_record(rec0, (uint32_t)te, rl);
             }
 #pragma unroll
             for (int e = 0; e < NE; e++) {
@@ -521,9 +542,8 @@ __device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm
 }
 
 template <int Q, bool CLOSED>
-__device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm, const GFTab &gf, int cnt, float *app, uint8_t *ctov,
-                                            uint8_t *dec, size_t frame_app, size_t frame_ctov, const RecLane &rl, uint64_t pol_first,
-                                            bool minform, bool decide, int lane)
+__device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm, const GFTab &gf, int cnt, char *app, char *ctov,
+                                            uint8_t *dec, const RecLane &rl, uint64_t pol_first, bool minform, bool decide, int lane)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     const Lists &ls = wm.ls;
@@ -533,10 +553,11 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
     __syncwarp();
     for (int c = 0; c < cnt; c++) {
         const int4 mt = wm.meta[c];
-        const int e0 = mt.x, dc = mt.y;
-        float *app_f = app + mt.z * frame_app;
-        uint8_t *ctov_f = ctov + mt.z * frame_ctov;
-        uint8_t *dec_f = dec + mt.z * a.N;
+        const int dc = TileMeta::dc(mt);
+        char *app_f = app + (uint32_t)mt.y;
+        uint8_t *rec0 = reinterpret_cast<uint8_t *>(ctov) + (uint32_t)mt.z;
+        /* output list of edge t (id_out): t = dc-1 -> F after dc-2 steps, else B / merge number 3dc-5+t; as an index into the tile's lists */
+        const int obase = dc > 2 ? ls.r0 + c * ls.lr - dc : c * dcm;
         for (int t = 0; t < dc; t += NE) {
             float v[NE][VPL];
             uint32_t ei[NE];
@@ -545,29 +566,31 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
             for (int e = 0; e < NE; e++) {
                 const int te = min(t + e, dc - 1);
                 ei[e] = wm.ew[c * dcm + te];
-                load_row_hint<Q>(app_f + (size_t)((ei[e] & 0xfffffu) * (uint32_t)Q), lane, v[e], pol_first);    /* parked Mvc, or the APP row again */
-                if (!NB_PARK_MVC) old[e] = load_record(ctov_f, (uint32_t)(e0 + te), rl);
+                load_row_hint<Q>(reinterpret_cast<const float *>(app_f + (ei[e] & 0xfffffu) * (uint32_t)(Q * 4)), lane, v[e], pol_first);    /* parked Mvc, or the APP row again */
+                if (!NB_PARK_MVC) old[e] = load_record(rec0, (uint32_t)te, rl);
             }
 #pragma unroll
             for (int e = 0; e < NE; e++) {
                 if (t + e < dc) {
-                    const uint32_t ed = (uint32_t)(e0 + t + e), var = ei[e] & 0xfffffu;
+                    const uint32_t var = ei[e] & 0xfffffu;
                     if (!NB_PARK_MVC) {
                         float cv[VPL];
                         expand_record<Q>(old[e], lane, wm.row3[e], cv, minform);
 #pragma unroll
                         for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334, same operands as phase 1 */
                     }
-                    const RecView nr = finish_list<Q, CLOSED>(ls, ls.idx(c, id_out(dc, t + e), dc), (ei[e] >> 20) & 0xff, gf, a.offset, lane);
-                    store_record(ctov_f, ed, rl, nr, n_m, lane);
+                    const int te = t + e;
+                    const int li = dc > 2 ? obase + (te == dc - 1 ? 2 * dc - 3 : 3 * dc - 5 + te) : obase + (1 - te);
+                    const RecView nr = finish_list<Q, CLOSED>(ls, li, (ei[e] >> 20) & 0xff, gf, a.offset, lane);
+                    store_record(rec0, (uint32_t)te, rl, nr, n_m, lane);
                     float mcv[VPL];
                     expand_record<Q>(nr, lane, wm.row3[e], mcv, minform);    /* :262-281 */
 #pragma unroll
                     for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
-                    store_row_hint<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v[e], pol_first);
+                    store_row_hint<Q>(reinterpret_cast<float *>(app_f + var * (uint32_t)(Q * 4)), lane, v[e], pol_first);
                     if (decide && (ei[e] >> 28)) {                                         /* tools.c:312 fused */
                         const int d = warp_argmin<Q>(v[e], lane);
-                        if (lane == 0) dec_f[var] = (uint8_t)d;
+                        if (lane == 0) dec[(uint32_t)mt.w + var] = (uint8_t)d;
                     }
                 }
             }
@@ -605,6 +628,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
     uint8_t *dec = a.dec + (size_t)blockIdx.x * F * N;
     const size_t frame_dense = (size_t)a.E * Q;
     float *ctov_d = ECN == 1 ? a.ctov_dense + blockIdx.x * F * frame_dense : nullptr;
+    const uint32_t rec_bytes = ECN == 1 ? (uint32_t)(Q * 4) : (uint32_t)rs;      /* bytes of CtoV state per edge */
 
     for (;;) {
         __syncthreads();
@@ -654,13 +678,15 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                 if (lane < cnt) {
                     const int item = first + lane, f = item / ncn;
                     const uint32_t info = a.cninfo[c0 + item - f * ncn];
-                    wm.meta.set(lane, info & 0xffffff, s_done[f] ? 0 : (int)(info >> 24), f);
+                    const uint32_t e0 = info & 0xffffff;
+                    wm.meta.set(lane, (int)e0, s_done[f] ? 0 : (int)(info >> 24), (uint32_t)f * (uint32_t)(N * Q * 4),
+                                ((uint32_t)f * (uint32_t)a.E + e0) * rec_bytes, (uint32_t)(f * N));
                 }
                 __syncwarp();
                 for (int i = lane; i < cnt * dcm; i += 32) {   /* edge words of the tile: variable | coefficient | last-visit flag */
                     const int c = i / dcm, t = i - c * dcm;
                     const int4 mt = wm.meta[c];
-                    if (t < mt.y) wm.ew[i] = a.einfo[mt.x + t];
+                    if (t < TileMeta::dc(mt)) wm.ew[i] = a.einfo[TileMeta::e0(mt) + t];
                 }
                 __syncwarp();
                 if constexpr (ECN == 0) {
@@ -668,13 +694,15 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                         const Lists &ls = wm.ls;
                         for (int c = 0; c < cnt; c++) {
                             const int4 mt = wm.meta[c];
-                            const int e0 = mt.x, dc = mt.y;
-                            float *app_f = app + mt.z * frame_app;
-                            const uint8_t *ctov_f = ctov + mt.z * frame_ctov;
+                            const int e0 = TileMeta::e0(mt), dc = TileMeta::dc(mt);
+                            float *app_f = reinterpret_cast<float *>(reinterpret_cast<char *>(app) + (uint32_t)mt.y);
+                            const uint8_t *ctov_f = ctov + (uint32_t)mt.z - (size_t)e0 * rs;
                             if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
                             if (NB_L2_PREFETCH && c + 1 < cnt) {
                                 const int4 nx = wm.meta[c + 1];
-                                if (nx.y > 0) prefetch_edges<Q>(app + nx.z * frame_app, ctov + nx.z * frame_ctov, a.einfo, nx.x, min(NE, nx.y), rs, lane);
+                                if (TileMeta::dc(nx) > 0) prefetch_edges<Q>(reinterpret_cast<float *>(reinterpret_cast<char *>(app) + (uint32_t)nx.y),
+                                                                            ctov + (uint32_t)nx.z - (size_t)TileMeta::e0(nx) * rs, a.einfo, TileMeta::e0(nx),
+                                                                            min(NE, TileMeta::dc(nx)), rs, lane);
                             }
                             gf16_phase1<CLOSED>(wm, gf, c, e0, dc, dcm, app_f, ctov_f, a.einfo, n_m, rs, lane, a.slow_counter);
                         }
@@ -682,23 +710,25 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                         tile_elementary_steps<Q>(ls, wm.meta, cnt, dcm, wm.mask, lane, a.nb_oper);
                         for (int c = 0; c < cnt; c++) {
                             const int4 mt = wm.meta[c];
-                            gf16_phase3<CLOSED>(wm, gf, c, mt.x, mt.y, dcm, app + mt.z * frame_app, ctov + mt.z * frame_ctov, dec + mt.z * N, n_m, rs, a.offset, lane);
+                            const int e0 = TileMeta::e0(mt);
+                            gf16_phase3<CLOSED>(wm, gf, c, e0, TileMeta::dc(mt), dcm, reinterpret_cast<float *>(reinterpret_cast<char *>(app) + (uint32_t)mt.y),
+                                                ctov + (uint32_t)mt.z - (size_t)e0 * rs, dec + (uint32_t)mt.w, n_m, rs, a.offset, lane);
                         }
                     } else {
-                        tile_phase1<Q, CLOSED>(a, wm, gf, cnt, app, ctov, frame_app, frame_ctov, rl, pol_stream, pol_keep, minform, lane);
+                        tile_phase1<Q, CLOSED>(a, wm, gf, cnt, reinterpret_cast<const char *>(app), reinterpret_cast<const char *>(ctov), rl, pol_stream, pol_keep, minform, lane);
                         tile_elementary_steps<Q>(wm.ls, wm.meta, cnt, dcm, wm.mask, lane, a.nb_oper);
-                        tile_phase3<Q, CLOSED>(a, wm, gf, cnt, app, ctov, dec, frame_app, frame_ctov, rl, pol_stream, minform, decide, lane);
+                        tile_phase3<Q, CLOSED>(a, wm, gf, cnt, reinterpret_cast<char *>(app), reinterpret_cast<char *>(ctov), dec, rl, pol_stream, minform, decide, lane);
                     }
                 } else {
                     /* ---------------- syndrome-based check node: one node at a time per warp ---------------- */
                     const SyndMem sm = make_synd_mem(smem, a, warp);
                     for (int c = 0; c < cnt; c++) {
                         const int4 mt = wm.meta[c];
-                        const int e0 = mt.x, dc = mt.y;
+                        const int dc = TileMeta::dc(mt);
                         if (dc == 0) continue;
-                        float *app_f = app + mt.z * frame_app;
-                        float *cd_f = ctov_d + mt.z * frame_dense;
-                        uint8_t *dec_f = dec + mt.z * N;
+                        float *app_f = reinterpret_cast<float *>(reinterpret_cast<char *>(app) + (uint32_t)mt.y);
+                        float *cd0 = reinterpret_cast<float *>(reinterpret_cast<char *>(ctov_d) + (uint32_t)mt.z);     /* dense CtoV row of the node's edge 0 */
+                        uint8_t *dec_f = dec + (uint32_t)mt.w;
                         /* V->C messages of the node: Mvc = APP - CtoV, truncation, rotation (NB_LDPC.c:329-374, syndrome_decoder.c:41-48) */
                         for (int t = 0; t < dc; t += NE) {
                             float v[NE][VPL];
@@ -706,12 +736,11 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
 #pragma unroll
                             for (int e = 0; e < NE; e++) {
                                 const int te = min(t + e, dc - 1);
-                                const uint32_t ed = (uint32_t)(e0 + te);
                                 const uint32_t ei = wm.ew[c * dcm + te];
                                 hv[e] = (ei >> 20) & 0xff;
                                 float cv[VPL];
                                 load_row<Q>(app_f + (size_t)((ei & 0xfffffu) * (uint32_t)Q), lane, v[e]);
-                                load_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, cv);
+                                load_row<Q>(cd0 + (size_t)((uint32_t)te * (uint32_t)Q), lane, cv);
 #pragma unroll
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);
                             }
@@ -736,16 +765,16 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                             if ((d & 3) == 0) synd_walk(sm, d, min(4, dc - d), a.offset, lane);
                             const uint32_t out = sm.key[0] + 1024 * (d & 3);
                             const int t = (int)lds_u32(sm.perm + 4 * d);                   /* un-permute, syndrome_decoder.c:234-253 */
-                            const uint32_t ed = (uint32_t)(e0 + t);
                             const uint32_t ei = wm.ew[c * dcm + t];
                             const uint32_t var = ei & 0xfffffu;
+                            float *cdrow = cd0 + (size_t)((uint32_t)t * (uint32_t)Q);
                             float mcv[VPL], v[VPL], cv[VPL];
                             synd_dense_row<Q, CLOSED>(out, gf, (ei >> 20) & 0xff, lane, mcv);
                             load_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v);
-                            load_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, cv);
+                            load_row<Q>(cdrow, lane, cv);
 #pragma unroll
                             for (int j = 0; j < VPL; j++) v[j] = __fadd_rn(mcv[j], __fsub_rn(v[j], cv[j]));   /* NB_LDPC.c:334, 448 */
-                            store_row<Q>(cd_f + (size_t)(ed * (uint32_t)Q), lane, mcv);                   /* NB_LDPC.c:438 */
+                            store_row<Q>(cdrow, lane, mcv);                   /* NB_LDPC.c:438 */
                             store_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v);
                             if (decide && (ei >> 28)) {
                                 const int dd = warp_argmin<Q>(v, lane);
@@ -860,7 +889,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
             sts_u8(ls.sym(list) + k, (uint32_t)gf_rot_in<Q, CLOSED>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]));
             if (k == 0) sts_u8(ls.len(li), (uint32_t)n_m);
         }
-        if (lane < cnt) wm.meta.set(lane, e0, dc, 0);
+        if (lane < cnt) wm.meta.set(lane, e0, dc, 0u, 0u, 0u);
         __syncwarp();
         tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
         fill_row<Q>(wm.row3[0], lane, NB_ROW_CLEAN);       /* aliases the input lists, dead after the elementary steps (degree 2: a region of its own) */
@@ -1094,7 +1123,7 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     /* per-warp small area: ES mask (q = 256) | meta | edge words | list lengths */
     int wa = 0;
     k.wa_mask = wa; wa += (k.q > 64 && k.ecn == 0) ? 8 * 32 * 4 : 0;
-    k.wa_meta = wa; wa += cpw * 8;
+    k.wa_meta = wa; wa += cpw * 16;
     k.wa_einfo = wa; wa += cpw * k.dc_max * 4;
     k.wa_len = wa; wa += align_up(cpw * k.L, 4);
     k.wa_bytes = align_up(wa, 16);

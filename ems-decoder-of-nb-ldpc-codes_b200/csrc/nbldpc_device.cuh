@@ -4,7 +4,7 @@
  * Building blocks (reference lines they replace):
  *   expand_record    bubble_decoder.c:262-270   dense q-vector of one stored C->V message
  *   select_edges     NB_LDPC.c:354-374          stable top-n_m of q values + normalisation, one warp
- *                                               per edge, NE edges interleaved for latency hiding
+ *                                               per edge, NEDG edges interleaved for latency hiding
  *   es_serial        bubble_decoder.c:316-593   ElementaryStep, one THREAD per step (32 per warp)
  *   warp_argmin      tools.c:312-330            Decision
  * GF symbols travel through the check node as BINARY IMAGES so that GF addition is XOR
@@ -280,7 +280,7 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
 }
 
 /*
- * Truncation of V->C messages (NB_LDPC.c:354-374) for NE edges at once: the n_m smallest of the q
+ * Truncation of V->C messages (NB_LDPC.c:354-374) for NEDG edges at once: the n_m smallest of the q
  * values mvc[e][], ascending, ties -> lowest symbol, values >= 1e5 never selected (slot keeps
  * (1e5, symbol 0) and symbol 0 is masked), then LLR[k] -= LLR[0], LLR[0] = 0.
  *
@@ -291,7 +291,7 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
  * one REDUX.MIN over the lane heads pop the global minimum, the owning lane stepping to its next row;
  * every lane then re-reads its head row, so the load needs no predicate and no copy.  The minimum comes
  * back warp-uniform, so lane r simply keeps the result of round r (NB_SEL_CAPTURE = 1: one compare + select, no
- * shared-memory traffic) or the winner stores it to sel[r] (NB_SEL_CAPTURE = 0).  The NE independent
+ * shared-memory traffic) or the winner stores it to sel[r] (NB_SEL_CAPTURE = 0).  The NEDG independent
  * REDUX chains are interleaved so that their latencies overlap.  The dropped low bits of the winners come
  * from the owning lane by two shuffles (each lane keeps the low bytes of its VPL values packed in one or two
  * registers), so no dense row is written for the read-back.  A result is accepted only if (a) no value was
@@ -306,19 +306,26 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
 #ifndef NB_SEL_CAPTURE
 #define NB_SEL_CAPTURE 1
 #endif
-template <int Q, int NE>
-__device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::VPL], int lane, uint32_t *(&scr)[NE],
-                                             uint32_t *(&sel)[NE], int n_m, float (&out_llr)[NE], int (&out_sym)[NE],
+#ifndef NB_SEL_LOOKAHEAD
+#define NB_SEL_LOOKAHEAD 0     /* capture mode only; measured: no gain (226.7 vs 226.4 Mbit/s), one instruction more per round */
+#endif
+#if !NB_SEL_CAPTURE
+#undef NB_SEL_LOOKAHEAD
+#define NB_SEL_LOOKAHEAD 0
+#endif
+template <int Q, int NEDG>
+__device__ __forceinline__ void select_edges(const float (&mvc)[NEDG][QTraits<Q>::VPL], int lane, uint32_t *(&scr)[NEDG],
+                                             uint32_t *(&sel)[NEDG], int n_m, float (&out_llr)[NEDG], int (&out_sym)[NEDG],
                                              unsigned *slow_counter)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     constexpr int LOGQ = QTraits<Q>::LOGQ;
     const bool active = (Q >= 32) || lane < Q;
     const int rounds = (n_m + 1 < Q) ? n_m + 1 : Q;
-    uint32_t head[NE], nxt[NE], selp[NE], mine[NE], lo[NE][2];
-    bool bad[NE];
+    uint32_t head[NEDG], nk[NEDG], nxt[NEDG], selp[NEDG], mine[NEDG], lo[NEDG][2];
+    bool bad[NEDG];
 #pragma unroll
-    for (int e = 0; e < NE; e++) {
+    for (int e = 0; e < NEDG; e++) {
         uint32_t key[VPL];
         if constexpr (Q == 256) {
             /* key = value bits with the low byte replaced by the symbol: one PRMT per value */
@@ -346,11 +353,17 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         for (int j = 0; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
         scr[e][VPL * 32 + lane] = NB_KEY_INF;
         head[e] = key[0];
+#if NB_SEL_LOOKAHEAD
+        nk[e] = VPL > 1 ? key[VPL > 1 ? 1 : 0] : NB_KEY_INF;     /* the lane's next key is already in a register ... */
+        nxt[e] = smem_u32(scr[e] + 32 + lane);          /* ... and this is its row */
+#else
+        nk[e] = 0;
         nxt[e] = smem_u32(scr[e] + lane);              /* row of the lane's current head */
+#endif
         selp[e] = smem_u32(sel[e]);
         mine[e] = NB_KEY_INF;
     }
-    if constexpr (Q == 16 && NE == 2) {
+    if constexpr (Q == 16 && NEDG == 2) {
         /* GF(16): a row is one key per lane of a half warp.  Both edges are sorted at once, edge 0 in lanes 0-15 and edge 1 in
          * lanes 16-31, by a 16-wide bitonic network (10 exchanges) instead of 2 x 16 reduction rounds. */
         const uint32_t other = __shfl_sync(NB_FULL, head[1], lane & 15);
@@ -369,7 +382,23 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
         mine[1] = __shfl_sync(NB_FULL, x, 16 | (lane & 15));
     } else {
     /* no __syncwarp needed: every lane only reads back what it wrote itself */
-#if NB_SEL_CAPTURE
+#if NB_SEL_CAPTURE && NB_SEL_LOOKAHEAD
+/* the winner takes its next key from a register and reloads the one behind it: the shared-memory latency is off the
+ * REDUX -> compare -> REDUX chain (it only matters when the same lane wins twice in a row) */
+#define NB_SEL_ROUND(E, OFF)                                                                                   \
+    asm volatile("{\n\t"                                                                                        \
+                 ".reg .pred p, c;\n\t"                                                                         \
+                 ".reg .u32 m;\n\t"                                                                             \
+                 "redux.sync.min.u32 m, %0, 0xffffffff;\n\t"                                                    \
+                 "setp.eq.u32 p, %0, m;\n\t"                                                                    \
+                 "selp.u32 %0, %3, %0, p;\n\t"                                                                  \
+                 "@p add.u32 %1, %1, 128;\n\t"                                                                  \
+                 "ld.shared.u32 %3, [%1];\n\t"                                                                  \
+                 "setp.eq.u32 c, %4, " #OFF ";\n\t"                                                             \
+                 "selp.u32 %2, m, %2, c;\n\t"                                                                   \
+                 "}"                                                                                             \
+                 : "+r"(head[E]), "+r"(nxt[E]), "+r"(mine[E]), "+r"(nk[E]) : "r"(lr) : "memory")
+#elif NB_SEL_CAPTURE
 #define NB_SEL_ROUND(E, OFF)                                                                                   \
     asm volatile("{\n\t"                                                                                        \
                  ".reg .pred p, c;\n\t"                                                                         \
@@ -382,24 +411,41 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                  "selp.u32 %2, m, %2, c;\n\t"                                                                   \
                  "}"                                                                                             \
                  : "+r"(head[E]), "+r"(nxt[E]), "+r"(mine[E]) : "r"(lr) : "memory")
+#endif
+#if NB_SEL_CAPTURE
+/* the last round only has to name the (n_m+1)-th key for the boundary test: nothing is popped */
+#define NB_SEL_PEEK(E)                                                                                          \
+    asm volatile("{\n\t"                                                                                        \
+                 ".reg .pred c;\n\t"                                                                            \
+                 ".reg .u32 m;\n\t"                                                                             \
+                 "redux.sync.min.u32 m, %1, 0xffffffff;\n\t"                                                    \
+                 "setp.eq.u32 c, %2, 0;\n\t"                                                                    \
+                 "selp.u32 %0, m, %0, c;\n\t"                                                                   \
+                 "}"                                                                                             \
+                 : "+r"(mine[E]) : "r"(head[E]), "r"(lr))
+    const int full = rounds - 1;
     int r = 0;
     int lr = lane;                                    /* lane - r: lane r keeps the minimum of round r */
 #pragma unroll 1
-    for (; r + 3 <= rounds; r += 3) {                 /* n_m + 1 = 21 rounds for the usual n_m = 20: no remainder */
+    for (; r + 4 <= full; r += 4) {                   /* n_m = 20 or 16 full rounds: no remainder */
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 0);
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 1);
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 1);
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 2);
-        lr -= 3;
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 2);
+#pragma unroll
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 3);
+        lr -= 4;
     }
 #pragma unroll 1
-    for (; r < rounds; r++) {
+    for (; r < full; r++) {
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 0);
         lr -= 1;
     }
+#pragma unroll
+    for (int e = 0; e < NEDG; e++) NB_SEL_PEEK(e);
 #else
 #define NB_SEL_ROUND(E, OFF)                                                                                   \
     asm volatile("{\n\t"                                                                                        \
@@ -412,31 +458,45 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NE][QTraits<Q>::
                  "ld.shared.u32 %0, [%1];\n\t"                                                                  \
                  "}"                                                                                             \
                  : "+r"(head[E]), "+r"(nxt[E]) : "r"(selp[E]) : "memory")
+#define NB_SEL_PEEK(E)                                                                                          \
+    asm volatile("{\n\t"                                                                                        \
+                 ".reg .pred p;\n\t"                                                                            \
+                 ".reg .u32 m;\n\t"                                                                             \
+                 "redux.sync.min.u32 m, %0, 0xffffffff;\n\t"                                                    \
+                 "setp.eq.u32 p, %0, m;\n\t"                                                                    \
+                 "@p st.shared.u32 [%1], %0;\n\t"                                                               \
+                 "}"                                                                                             \
+                 :: "r"(head[E]), "r"(selp[E]) : "memory")
+    const int full = rounds - 1;
     int r = 0;
 #pragma unroll 1
-    for (; r + 3 <= rounds; r += 3) {
+    for (; r + 4 <= full; r += 4) {
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 0);
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 0);
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 4);
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 4);
 #pragma unroll
-        for (int e = 0; e < NE; e++) NB_SEL_ROUND(e, 8);
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 8);
 #pragma unroll
-        for (int e = 0; e < NE; e++) selp[e] += 12;
+        for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, 12);
+#pragma unroll
+        for (int e = 0; e < NEDG; e++) selp[e] += 16;
     }
 #pragma unroll 1
-    for (; r < rounds; r++) {
+    for (; r < full; r++) {
 #pragma unroll
-        for (int e = 0; e < NE; e++) { NB_SEL_ROUND(e, 0); selp[e] += 4; }
+        for (int e = 0; e < NEDG; e++) { NB_SEL_ROUND(e, 0); selp[e] += 4; }
     }
+#pragma unroll
+    for (int e = 0; e < NEDG; e++) NB_SEL_PEEK(e);
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < NE; e++) mine[e] = sel[e][min(lane, rounds - 1)];
+    for (int e = 0; e < NEDG; e++) mine[e] = sel[e][min(lane, rounds - 1)];
 #endif
     }
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < NE; e++) {
+    for (int e = 0; e < NEDG; e++) {
         /* lane k: k-th winner; lanes >= rounds hold a copy of the last one (or +inf), which no test below looks at */
         const uint32_t after = __shfl_down_sync(NB_FULL, mine[e], 1);
         const bool amb = lane < n_m && lane + 1 < rounds && ((mine[e] >> LOGQ) == (after >> LOGQ));

@@ -13,7 +13,7 @@ for V in $VARS; do
 import json
 try:
     j = json.load(open('gpurun_out/var_${WL}_$V.json'))
-    print('VARIANT', '$WL', '$V', 'value', round(j['value'], 2), 'Mbit/s kernel_ms', round(j['roofline']['kernel_ms'], 3), 'frac', round(j['roofline']['frac'], 4), 'clk', j['clocks']['sm_mhz'], j['geometry'])
+    print('VARIANT', '$WL', '$V', 'value', round(j['value'], 2), 'Mbit/s kernel_ms', round(j['roofline']['kernel_ms'], 3), 'frac', round(j['roofline']['frac'], 4), 'clk', j['clocks']['sm_mhz'], 'slow', j['counters']['slow_path_selects'], j['geometry'])
 except Exception as e:
     print('VARIANT', '$WL', '$V', 'FAILED rc=$RC', e)
 PY

@@ -503,6 +503,56 @@ def test_c_driver_reproduces_reference_console_and_results_file(args, ecn, conso
     assert (int(mf.group(1)), int(mf.group(2))) == (console[0], nfile), line
 
 
+@pytest.mark.parametrize("devices", ["0,0", "0-1", "all"])
+@pytest.mark.parametrize("args,ecn,console,nfile", KNOWN[:2])
+def test_c_driver_on_several_devices(args, ecn, console, nfile, devices, tmp_path):
+    """nbldpc_mc with one host thread + one context per device: frame blocks by drand48 jump-ahead, per-frame rows merged in
+    frame order (40-erroneous-frames rule), one ncclAllReduce of the counters.  "0,0" runs the threaded rounds with two
+    contexts on one GPU (no NCCL: a device cannot be two ranks); "0-1" and "all" need two or more GPUs."""
+    import re
+    import subprocess
+    ndev = nbldpc.device_count()
+    if devices != "0,0" and ndev < 2:
+        pytest.skip("needs two or more GPUs (run under gpurun --gpus 2 / 8)")
+    exe = os.path.join(os.path.dirname(nbldpc.LIB_PATH), "nbldpc_mc")
+    os.makedirs(tmp_path / "data")
+    a = list(args)
+    a[2] = matrix_path(a[2])
+    r = subprocess.run([exe] + a + ["96", devices, str(ecn), "1"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    m = re.findall(r"<(\d+)> FER=\s*(\d+)\s*/\s*(\d+)\s*=\s*[\d.]+\s*BER=\s*(\d+)\s*/\s*x\s*=\s*[\d.eE+-]+\s*avr_it=([\d.]+)", r.stdout)
+    assert m, r.stdout[-2000:]
+    last = m[-1]
+    assert (int(last[1]), int(last[2]), int(last[3]), last[4]) == console
+    if devices != "0,0":
+        assert "one ncclAllReduce" in r.stdout and ("devices: %d" % (2 if devices == "0-1" else ndev)) in r.stdout
+    line = list((tmp_path / "data").glob("results_*.txt"))[0].read_text()
+    mf = re.search(r"FER=\s*(\d+)\s*/\s*(\d+)", line)
+    assert (int(mf.group(1)), int(mf.group(2))) == (console[0], nfile), line
+
+
+def test_c_driver_stops_at_the_40th_erroneous_frame_in_frame_order(tmp_path):
+    """NB_LDPC.c:506: at a low SNR the run ends with the frame of the 40th error, whatever the batch size and the number of
+    contexts (frames decoded beyond it are dropped); one and two contexts must print the same last line."""
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(nbldpc.LIB_PATH), "nbldpc_mc")
+    outs = []
+    for devices, batch in (("0", "64"), ("0,0", "24"), ("0,0", "100")):
+        d = tmp_path / ("run_%s_%s" % (devices.replace(",", "_"), batch))
+        os.makedirs(d / "data")
+        r = subprocess.run([exe, "2000", "10", matrix_path("matrices/N96_K48_GF64"), "2.0", "20", "0.3", "25", batch, devices, "0", "1"], cwd=d,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:]
+        m = re.findall(r"<(\d+)> FER=\s*(\d+)\s*/\s*(\d+)\s*=\s*[\d.]+\s*BER=\s*(\d+)\s*/\s*x\s*=\s*[\d.eE+-]+\s*avr_it=([\d.]+)", r.stdout)
+        outs.append(m[-1])
+        assert int(m[-1][1]) == 40 and int(m[-1][2]) < 2000
+        line = list((d / "data").glob("results_*.txt"))[0].read_text()
+        mf = re.search(r"FER=\s*(\d+)\s*/\s*(\d+)", line)
+        assert (int(mf.group(1)), int(mf.group(2))) == (40, int(m[-1][2])), line            # results file: nb = frame of the 40th error
+    assert outs[0] == outs[1] == outs[2], outs
+
+
 def test_sharded_monte_carlo_on_the_gpu():
     multigpu = __import__("importlib").import_module("ems-decoder-of-nb-ldpc-codes_b200.multigpu")
     code = nbldpc.Code(matrix_path("matrices/N96_K48_GF64"))
