@@ -95,7 +95,7 @@ struct KArgs {
     int ecn, S, Spad, n_cv;
     const uint8_t *cfg;                 /* [S][dc_max] u8 */
     float *ctov_dense;                  /* [slots][E][q] f32 */
-    int off_cfg, sw_key, sw_pay, sw_gf, sw_hist, sw_M, sw_perm;   /* sw_*: offsets inside a warp's list area */
+    int off_cfg, sw_key, sw_pay, sw_gf, sw_hist, sw_cand, sw_M, sw_rows, sw_perm;   /* sw_*: offsets inside a warp's list area */
 };
 
 /* Lists of a warp's tile in shared memory, by 32-bit shared-window address: one array of cpw * L lists, the input lists
@@ -272,24 +272,24 @@ __device__ __forceinline__ void load_gf_tables(unsigned char *smem, const KArgs 
     gf.img = tab; gf.inv = tab + 256; gf.rotin = a.rotin; gf.rotout = a.rotout;
 }
 
-__device__ __forceinline__ int std_max_i(int a, int b) { return a > b ? a : b; }
 __device__ __forceinline__ SyndMem make_synd_mem(unsigned char *smem, const KArgs &a, int warp)
 {
     SyndMem sm;
     const uint32_t wb = smem_u32(smem + a.off_wb + warp * a.wb_bytes);
     sm.lists = wb + a.wb_U;
-    sm.key[0] = wb + a.sw_key; sm.key[1] = sm.key[0] + std_max_i(4 * a.Spad, 4096);   /* buffer 0 later holds 4 output rows of 256 f32 */
-    sm.pay[0] = wb + a.sw_pay; sm.pay[1] = sm.pay[0] + 2 * a.Spad;
-    sm.gf = wb + a.sw_gf; sm.hist = wb + a.sw_hist; sm.M = wb + a.sw_M; sm.perm = wb + a.sw_perm;
-    sm.cfg = smem_u32(smem + a.off_cfg);
-    sm.lstride = a.lstride; sm.n_m = a.n_m; sm.dc = a.dc_max; sm.S = a.S; sm.Spad = a.Spad; sm.n_cv = a.n_cv;
+    sm.gkey = wb + a.sw_key; sm.gpay = wb + a.sw_pay; sm.gfa = wb + a.sw_gf;
+    sm.hist = wb + a.sw_hist; sm.hsat = sm.gkey; sm.cand = wb + a.sw_cand;
+    sm.rows = wb + a.sw_rows; sm.keya = sm.rows;
+    sm.M = wb + a.sw_M; sm.perm = wb + a.sw_perm;
+    sm.cfg = smem_u32(smem + a.off_cfg); sm.cfgmask = sm.cfg + (uint32_t)(a.S * a.dc_max);
+    sm.lstride = a.lstride; sm.n_m = a.n_m; sm.dc = a.dc_max; sm.S = a.S; sm.n_cv = a.n_cv;
     return sm;
 }
 __device__ __forceinline__ void load_cfg_table(unsigned char *smem, const KArgs &a)
 {
     if (a.ecn != 1) return;
     uint8_t *dst = smem + a.off_cfg;
-    for (int i = threadIdx.x; i < a.S * a.dc_max; i += blockDim.x) dst[i] = a.cfg[i];
+    for (int i = threadIdx.x; i < a.S * (a.dc_max + 1); i += blockDim.x) dst[i] = a.cfg[i];      /* table, then one membership byte per configuration */
 }
 /* dense output row of one edge from the syndrome check node: Mcv[s] = M[img(MULGF[s][h])] (syndrome_decoder.c:260-266
  * followed by the scatter NB_LDPC.c:415-421) */
@@ -760,10 +760,9 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                         }
                         __syncwarp();
                         synd_prepare(sm, lane);
-                        synd_sats(sm, lane);
                         for (int d = 0; d < dc; d++) {
                             if ((d & 3) == 0) synd_walk(sm, d, min(4, dc - d), a.offset, lane);
-                            const uint32_t out = sm.key[0] + 1024 * (d & 3);
+                            const uint32_t out = sm.rows + 1024 * (d & 3);
                             const int t = (int)lds_u32(sm.perm + 4 * d);                   /* un-permute, syndrome_decoder.c:234-253 */
                             const uint32_t ei = wm.ew[c * dcm + t];
                             const uint32_t var = ei & 0xfffffu;
@@ -933,10 +932,9 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_synd_kernel(const KArgs a
         }
         __syncwarp();
         synd_prepare(sm, lane);
-        synd_sats(sm, lane);
         for (int d = 0; d < dc; d++) {
             if ((d & 3) == 0) synd_walk(sm, d, min(4, dc - d), a.offset, lane);
-            const uint32_t out = sm.key[0] + 1024 * (d & 3);
+            const uint32_t out = sm.rows + 1024 * (d & 3);
             const int t = (int)lds_u32(sm.perm + 4 * d);
             float *dst = cllr + ((size_t)b * dc + t) * Q;
             int *gdst = cgf + ((size_t)b * dc + t) * Q;
@@ -1125,7 +1123,7 @@ static void plan_smem(KArgs &k, int nw, int cpw)
     k.wa_mask = wa; wa += (k.q > 64 && k.ecn == 0) ? 8 * 32 * 4 : 0;
     k.wa_meta = wa; wa += cpw * 16;
     k.wa_einfo = wa; wa += cpw * k.dc_max * 4;
-    k.wa_len = wa; wa += align_up(cpw * k.L, 4);
+    k.wa_len = wa; wa += k.ecn == 0 ? align_up(cpw * k.L, 4) : 0;
     k.wa_bytes = align_up(wa, 16);
     k.off_wa = off; off += nw * k.wa_bytes;
     k.lstride = align_up(5 * k.n_m, 4);
@@ -1142,18 +1140,20 @@ static void plan_smem(KArgs &k, int nw, int cpw)
         else { k.wb_scr3 = align_up(total, 16); total = k.wb_scr3 + s3; }   /* ... unless they do not fit, or degree 2: the output lists ARE input lists */
         k.wb_bytes = align_up(total, 16);
     } else {
-        /* syndrome check node: CTA-wide configuration table, then per warp: lists | scratch/keys x2 | payload x2 | gf | hist | M | perm */
-        k.off_cfg = off; off += align_up(k.S * k.dc_max, 16);
+        /* syndrome check node: CTA-wide configuration table, then per warp: lists | grouped keys (aliased by the selection scratch of
+         * phase 1, dead once the node's lists are written) | grouped configuration indices | histograms / output rows | group starts | perm */
+        k.off_cfg = off; off += align_up(k.S * (k.dc_max + 1), 16);
         int wb2 = 0;
         k.wb_U = wb2; k.wb_R = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
-        /* the selection scratch of phase 1 is dead once the node's lists are written: it aliases the sort buffers */
         k.wb_scr1 = wb2; k.wb_scr3 = wb2;
-        k.sw_key = wb2; wb2 += std::max(2 * std::max(4 * k.Spad, 4096), align_up(sq, 16));
-        k.sw_pay = wb2; wb2 += 2 * 2 * k.Spad;
-        k.sw_gf = wb2; wb2 += k.Spad;
-        k.sw_hist = wb2; wb2 += 256 * 4;
-        k.sw_M = wb2; wb2 += 256 * 4;
-        k.sw_perm = wb2; wb2 += 128;         /* perm[16] i32 | sat[16] f32 */
+        k.sw_key = wb2; wb2 += std::max(std::max(align_up(4 * k.S, 16), align_up(sq, 16)), ((k.dc_max + 1) / 2) * 1024);   /* grouped keys | saturation histograms | selection scratch */
+        k.sw_pay = wb2; wb2 += align_up(2 * k.S, 16);
+        k.sw_gf = wb2; wb2 += align_up(k.S, 16);
+        k.sw_hist = wb2; wb2 += 1024;                                                    /* symbol histogram / cursors */
+        k.sw_cand = wb2; wb2 += k.dc_max * NB_SYND_CAND * 4;
+        k.sw_rows = wb2; wb2 += std::max(4096, align_up(4 * k.S, 16));                   /* syndromes by configuration, then the 4 output rows */
+        k.sw_M = wb2; wb2 += align_up(257 * 2, 16);
+        k.sw_perm = wb2; wb2 += NB_SYND_PERM_BYTES;
         k.wb_bytes = align_up(wb2, 16);
     }
     k.off_wb = off; off += nw * k.wb_bytes;
@@ -1231,10 +1231,13 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
         int *tab = nbgpu_build_config_table(dc, d1, d2, d3, trunc, &size);
         if (!tab || size < 1) { ctx_err(c, "cannot build the configuration table"); nbgpu_destroy(c); return NBGPU_ENOMEM; }
         if (size > NB_SYND_MAX) { free(tab); ctx_err(c, "%d configurations: at most %d are supported (use cfg_trunc)", size, NB_SYND_MAX); nbgpu_destroy(c); return NBGPU_EINVAL; }
-        cfg8.resize((size_t)size * dc);
+        cfg8.assign((size_t)size * (dc + 1), 0);          /* table [size][dc], then per configuration the edges it does not deviate on */
         for (int d = 0; d < dc; d++) {
             int kept = 0;
-            for (int i = 0; i < size; i++) { cfg8[(size_t)i * dc + d] = (uint8_t)tab[(size_t)i * dc + d]; kept += tab[(size_t)i * dc + d] == 0; }
+            for (int i = 0; i < size; i++) {
+                cfg8[(size_t)i * dc + d] = (uint8_t)tab[(size_t)i * dc + d];
+                if (tab[(size_t)i * dc + d] == 0) { kept++; cfg8[(size_t)size * dc + i] |= (uint8_t)(1u << d); }
+            }
             if (n_cv - 1 + 3 * d >= kept) { free(tab); ctx_err(c, "n_cv=%d: edge %d has only %d decorrelated syndromes, index %d is read (syndrome_decoder.c:195)", n_cv, d, kept, n_cv - 1 + 3 * d); nbgpu_destroy(c); return NBGPU_EINVAL; }
         }
         free(tab);

@@ -7,33 +7,50 @@
  *      (selection with strict '<': ties keep the lower index first);
  *   2. one syndrome per configuration: LLR = f32 sum over the (presorted) edges of the list entry the
  *      configuration names, GF = sum (XOR of binary images) of the entries' symbols;
- *   3. STABLE sort of the syndromes by LLR -- the reference's insertion sort; here a stable LSD radix
- *      sort of the f32 bit patterns (all LLRs are non-negative) with the configuration index as payload;
- *   4. per edge d (presorted position): walk the sorted syndromes whose configuration does not deviate on
- *      d ("decorrelation"), add the edge's best symbol, first hit of a symbol sets its LLR, later hits
- *      go through bayes() in order; saturation at the LLR of decorrelated syndrome n_cv-1+3d, + offset.
- *      Hits of different symbols never interact, so a fifth stable radix pass groups the sorted list by symbol
- *      and every lane replays the hits of its own eight symbols -- same order inside a symbol, no conflicts.
+ *   3. the reference then sorts ALL syndromes by LLR (stable insertion sort) and, per edge d, walks the sorted
+ *      syndromes whose configuration does not deviate on d ("decorrelation"): the first hit of a symbol sets its
+ *      LLR, later hits go through bayes() in order; saturation at the LLR of decorrelated syndrome n_cv-1+3d, + offset.
+ *
+ * What the walk needs from that global order is much less than a sort of ~1000 keys:
+ *   (a) hits of DIFFERENT symbols never interact, so only the order INSIDE a symbol group matters: one counting pass
+ *       groups the syndromes by symbol (shared-memory histogram + cursor), and every lane orders its own eight groups
+ *       (3.7 entries on average) by (LLR, configuration index) with an insertion sort -- exactly the order a stable
+ *       sort by LLR leaves inside the group;
+ *   (b) the saturation level of edge d is an ORDER STATISTIC: the (n_cv-1+3d)-th smallest LLR among the syndromes
+ *       decorrelated on d.  A 256-bin histogram over a monotone 8-bit quantisation of the LLR (one per edge, filled in
+ *       the same pass that computes the syndromes) names the bin that holds it; the few syndromes of that bin are
+ *       collected and ranked exactly.  (More candidates than the collection buffer holds: a bitwise search with
+ *       warp-wide counts, exact for any input.)
+ * The round-1 kernel spent five 945-key LSD radix passes (MATCH-ranked scatters, 30 % of its instructions and most of its
+ * latency) to obtain the same two things.  All LLRs are non-negative, so float order == bit-pattern order.
  * Symbols are binary images (GF addition == XOR) exactly as in the bubble path.
  */
 #pragma once
 #include "nbldpc_device.cuh"
 
-#define NB_SYND_MAX 1024                 /* configurations per check node the shared-memory plan supports */
+#define NB_SYND_MAX 1024                 /* configurations per check node: 32 per lane, kept in registers */
+#define NB_SYND_CAND 32                  /* candidates per edge collected for the exact saturation level (more: bitwise search) */
 
 /* a warp's shared memory for the syndrome check node, by shared-window address */
 struct SyndMem {
-    uint32_t lists;      /* dc lists: n_m f32 | n_m u8 (stride lstride) in ORIGINAL edge order        */
-    uint32_t key[2];     /* [Spad] u32 sort keys (ping-pong)                                           */
-    uint32_t pay[2];     /* [Spad] u16 configuration index (ping-pong)                                 */
-    uint32_t gf;         /* [Spad] u8 syndrome symbol, indexed by configuration                        */
-    uint32_t hist;       /* [256] u32 radix histogram; afterwards f32 output LLRs of the current edge,
-                            indexed by binary image                                                      */
-    uint32_t M;          /* [256] u32 first position of every symbol group in the symbol-grouped order    */
-    uint32_t perm;       /* [16] i32: original edge at presorted position i; [16] = sat of the current edge */
-    uint32_t cfg;        /* [S][dc] u8 configuration table (shared by the CTA)                          */
-    int lstride, n_m, dc, S, Spad, n_cv;
+    uint32_t lists;      /* dc lists: n_m f32 | n_m u8 (stride lstride) in ORIGINAL edge order                          */
+    uint32_t gkey;       /* [S] u32 syndrome LLR bits, grouped by symbol, every group ascending in (LLR, configuration)  */
+    uint32_t gpay;       /* [S] u16 configuration index of the same entries                                               */
+    uint32_t gfa;        /* [S] u8 syndrome symbol by configuration index                                                 */
+    uint32_t M;          /* [257] u16 first position of every symbol group                                                */
+    uint32_t rows;       /* 4 output rows of 256 f32 (indexed by binary image); before the walk the same bytes hold        */
+    uint32_t keya;       /*   [S] u32 syndrome LLR bits by configuration index                                             */
+    uint32_t hist;       /* [256] u32 symbol histogram / scatter cursors                                                   */
+    uint32_t hsat;       /* [ceil(dc/2)][256] u32 per-bin counts of the decorrelated syndromes, two edges per word (16+16
+                            bits); the same bytes as gkey, which is only written once the saturation bins are known        */
+    uint32_t cand;       /* [dc][NB_SYND_CAND] u32 candidates of the saturation bins                                       */
+    uint32_t perm;       /* [16] i32 original edge at presorted position i | [16] f32 saturation level | [16] i32 saturation bin |
+                            [16] i32 syndromes below that bin | [16] i32 candidate counters                                */
+    uint32_t cfg;        /* [S][dc] u8 configuration table (shared by the CTA)                                             */
+    uint32_t cfgmask;    /* [S] u8: bit d set = the configuration does not deviate on presorted edge d (syndrome_decoder.c:96-98) */
+    int lstride, n_m, dc, S, n_cv;
 };
+#define NB_SYND_PERM_BYTES 320
 
 /* bayes(M1 = new LLR, M2 = current LLR), syndrome_decoder.c:2142-2211.  The reference takes double arguments, keeps float
  * locals and multiplies by double constants.  Bit-exact equivalents used here:
@@ -41,32 +58,53 @@ struct SyndMem {
  *   - dif = (float)(M2 - M1): the double difference is kept (one DADD), then rounded;
  *   - (double)dif < 0.1 / 0.2 / 1 / 2  ==  dif < 0.1f / 0.2f / 1.0f / 2.0f  (0.1f and 0.2f are the first floats above 0.1, 0.2);
  *   - (float)(c * (double)min) for c = 0.5, 0.75, 0.9375: the double product of a float by a 1-4 bit constant is exact, so its
- *     rounding equals the float product; c = 0.825 is not representable and keeps the double multiplication. */
-__device__ __forceinline__ float synd_bayes(float m1, float m2)
+ *     rounding equals the float product; c = 0.825 is not representable and keeps the double multiplication.
+ * Branch-free: every lane of the walk evaluates it on every hit, so divergence would cost more than the few extra instructions. */
+__device__ __forceinline__ float synd_bayes_sel(float m1, float m2)
 {
-    const bool lt = m1 < m2;
-    float mn = lt ? m1 : m2;
-    const float hi = lt ? m2 : m1;
+    const float mn = fminf(m1, m2), hi = fmaxf(m1, m2);          /* M1 < M2 ? (M1, M2) : (M2, M1); equal values give the same pair */
     const float dif = __double2float_rn(__dsub_rn((double)hi, (double)mn));
-    if (dif < 0.1f) mn = __fmul_rn(0.5f, mn);
-    else if (dif < 0.2f) mn = __fmul_rn(0.75f, mn);
-    else if (dif < 1.0f) mn = __double2float_rn(__dmul_rn(0.825, (double)mn));
-    else if (dif < 2.0f) mn = __fmul_rn(0.9375f, mn);
-    return mn;
+    const float f = dif < 0.1f ? 0.5f : dif < 0.2f ? 0.75f : dif < 2.0f ? 0.9375f : 1.0f;
+    const float a = __fmul_rn(f, mn);
+    const float b = __double2float_rn(__dmul_rn(0.825, (double)mn));
+    return (dif >= 0.2f && dif < 1.0f) ? b : a;
 }
 
-/* 5th radix pass: the digit is the syndrome's symbol (padding entries go to group 255 and sort last inside it) */
-__device__ __forceinline__ uint32_t synd_symbol_digit(const SyndMem &sm, int src, int i)
+/* monotone 8-bit quantisation of a non-negative float: 16 bins per octave from 2^-4 upwards (bin 0: below, bin 255: beyond
+ * 2^-4 * 2^(254/16)); any monotone map is correct, the resolution only decides how many candidates share the target bin */
+__device__ __forceinline__ uint32_t synd_bin(uint32_t bits)
 {
-    unsigned short p;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[src] + 2 * i));
-    return (int)p < sm.S ? lds_u8(sm.gf + p) : 255u;
+    const int q = (int)(bits >> 19) - ((123 << 4) - 1);
+    return (uint32_t)min(max(q, 0), 255);
 }
 
-/* steps 1-3: after this call key[0]/pay[0] hold the syndromes in the reference's sorted order */
+__device__ __forceinline__ uint32_t synd_M(const SyndMem &sm, uint32_t g)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(sm.M + 2 * g));
+    return v;
+}
+/* first symbol group of lane L's share of the symbol-grouped order: the lanes take runs of whole groups of (almost) equal
+ * length, S/32 entries each, instead of eight groups each (whose sizes vary by a factor of three) */
+__device__ __forceinline__ int synd_lane_group(const SyndMem &sm, int lane)
+{
+    const uint32_t want = (uint32_t)(sm.S * lane) >> 5;
+    int lo = 0, hi = 256;                                        /* smallest g with M[g] >= want; M[256] = S >= want */
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int mid = (lo + hi) >> 1;
+        if (synd_M(sm, (uint32_t)mid) >= want) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+/*
+ * Everything up to the walk.  On return: gkey/gpay hold the syndromes grouped by symbol, every group in the reference's
+ * sorted order; M[g] the group starts; perm[0..dc) the presorting; perm+64 the dc saturation levels (:195).
+ */
 __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
 {
-    const int dc = sm.dc, n_m = sm.n_m;
+    const int dc = sm.dc, n_m = sm.n_m, S = sm.S;
     /* ---- presorting_mvc ---- */
     {
         const int i = lane < dc ? lane : 0;
@@ -88,67 +126,61 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
         }
         __syncwarp();
         if (lane < 4) sts_u32(sm.perm + 4 * rank2, (uint32_t)e);
+        /* histograms and counters start at zero */
+        for (int w = lane; w < 256; w += 32) sts_u32(sm.hist + 4 * w, 0u);
+        for (int w = lane; w < ((dc + 1) >> 1) * 256; w += 32) sts_u32(sm.hsat + 4 * w, 0u);
+        if (lane < 16) sts_u32(sm.perm + 256 + 4 * lane, 0u);
         __syncwarp();
     }
-    /* ---- syndromes, :64-77 ---- */
+    /* ---- syndromes (:64-77) + symbol histogram + saturation histograms, one pass ---- */
     if (dc == 4) {                                   /* the usual degree: list bases in registers, one table word per configuration */
         uint32_t lb[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) lb[j] = sm.lists + lds_u32(sm.perm + 4 * j) * sm.lstride;
-        for (int i = lane; i < sm.Spad; i += 32) {
-            uint32_t key = 0xffffffffu, pay = 0xffffu;
-            if (i < sm.S) {
-                const uint32_t cw = lds_u32(sm.cfg + 4 * i);
-                float llr = 0.0f;
-                uint32_t gf = 0;
+#pragma unroll 2
+        for (int i = lane; i < S; i += 32) {
+            const uint32_t cw = lds_u32(sm.cfg + 4 * i), mem = lds_u8(sm.cfgmask + i);
+            float llr = 0.0f;
+            uint32_t gf = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t c = (cw >> (8 * j)) & 255u;
-                    llr = __fadd_rn(llr, lds_f32(lb[j] + 4 * c));
-                    gf ^= lds_u8(lb[j] + 4 * n_m + c);
-                }
-                key = __float_as_uint(llr); pay = (uint32_t)i;
-                sts_u8(sm.gf + i, gf);
+            for (int j = 0; j < 4; j++) {
+                const uint32_t c = (cw >> (8 * j)) & 255u;
+                llr = __fadd_rn(llr, lds_f32(lb[j] + 4 * c));
+                gf ^= lds_u8(lb[j] + 4 * n_m + c);
             }
-            sts_u32(sm.key[0] + 4 * i, key);
-            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[0] + 2 * i), "h"((unsigned short)pay) : "memory");
+            const uint32_t bits = __float_as_uint(llr), bin = synd_bin(bits);
+            sts_u32(sm.keya + 4 * i, bits);
+            sts_u8(sm.gfa + i, gf);
+            asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(sm.hist + 4 * gf) : "memory");
+            /* one word per bin and PAIR of edges, 16 bits each */
+            const uint32_t inc0 = (mem & 1u) | ((mem & 2u) << 15), inc1 = ((mem >> 2) & 1u) | ((mem & 8u) << 13);
+            if (inc0) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(sm.hsat + 4 * bin), "r"(inc0) : "memory");
+            if (inc1) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(sm.hsat + 1024 + 4 * bin), "r"(inc1) : "memory");
         }
     } else {
-        for (int i = lane; i < sm.Spad; i += 32) {
-            uint32_t key = 0xffffffffu, gf = 0, pay = 0xffffu;
-            if (i < sm.S) {
-                float llr = 0.0f;
-                for (int j = 0; j < dc; j++) {
-                    const uint32_t list = sm.lists + lds_u32(sm.perm + 4 * j) * sm.lstride;
-                    const uint32_t c = lds_u8(sm.cfg + i * dc + j);
-                    llr = __fadd_rn(llr, lds_f32(list + 4 * c));
-                    gf ^= lds_u8(list + 4 * n_m + c);
-                }
-                key = __float_as_uint(llr); pay = (uint32_t)i;
-                sts_u8(sm.gf + i, gf);
+        for (int i = lane; i < S; i += 32) {
+            const uint32_t mem = lds_u8(sm.cfgmask + i);
+            float llr = 0.0f;
+            uint32_t gf = 0;
+            for (int j = 0; j < dc; j++) {
+                const uint32_t list = sm.lists + lds_u32(sm.perm + 4 * j) * sm.lstride;
+                const uint32_t c = lds_u8(sm.cfg + i * dc + j);
+                llr = __fadd_rn(llr, lds_f32(list + 4 * c));
+                gf ^= lds_u8(list + 4 * n_m + c);
             }
-            sts_u32(sm.key[0] + 4 * i, key);
-            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[0] + 2 * i), "h"((unsigned short)pay) : "memory");
+            const uint32_t bits = __float_as_uint(llr), bin = synd_bin(bits);
+            sts_u32(sm.keya + 4 * i, bits);
+            sts_u8(sm.gfa + i, gf);
+            asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(sm.hist + 4 * gf) : "memory");
+            for (int p = 0; 2 * p < dc; p++) {
+                const uint32_t inc = ((mem >> (2 * p)) & 1u) | (((mem >> (2 * p + 1)) & 1u) << 16);
+                if (inc) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(sm.hsat + 1024 * p + 4 * bin), "r"(inc) : "memory");
+            }
         }
     }
     __syncwarp();
-    /* ---- stable LSD radix sort, 4 passes of 8 bits over the f32 bit pattern (sorting(), :1315-1334, is a stable insertion
-     * sort), then a 5th stable pass on the syndrome's symbol: buffer 0 ends up in the reference's sorted order, buffer 1
-     * grouped by symbol with every group still ascending in (LLR, sorted position) ---- */
-    const unsigned lt = (1u << lane) - 1u;
-    for (int pass = 0; pass < 5; pass++) {
-        const int src = pass & 1, dst = src ^ 1, shift = 8 * pass;
-#pragma unroll
-        for (int b = 0; b < 8; b++) sts_u32(sm.hist + 4 * (lane * 8 + b), 0u);
-        __syncwarp();
-        for (int i = lane; i < sm.Spad; i += 32) {
-            uint32_t d;
-            if (pass < 4) d = (lds_u32(sm.key[src] + 4 * i) >> shift) & 255u;
-            else d = synd_symbol_digit(sm, src, i);
-            asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(sm.hist + 4 * d) : "memory");
-        }
-        __syncwarp();
-        /* exclusive prefix sum over the 256 bins: lane owns bins 8*lane .. 8*lane+7 */
+    /* ---- group starts: exclusive prefix sum over the 256 symbol bins, lane owns bins 8*lane .. 8*lane+7 ---- */
+    {
         uint32_t h[8], tot = 0;
 #pragma unroll
         for (int b = 0; b < 8; b++) { h[b] = lds_u32(sm.hist + 4 * (lane * 8 + b)); tot += h[b]; }
@@ -157,92 +189,141 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(NB_FULL, inc, o); if (lane >= o) inc += t; }
         uint32_t run = inc - tot;
 #pragma unroll
-        for (int b = 0; b < 8; b++) { sts_u32(sm.hist + 4 * (lane * 8 + b), run); run += h[b]; }
-        if (pass == 4) {                                   /* group boundaries of the symbol-grouped order: start[256] + end */
-#pragma unroll
-            for (int b = 0; b < 8; b++) sts_u32(sm.M + 4 * (lane * 8 + b), lds_u32(sm.hist + 4 * (lane * 8 + b)));
+        for (int b = 0; b < 8; b++) {
+            sts_u32(sm.hist + 4 * (lane * 8 + b), run);
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.M + 2 * (lane * 8 + b)), "h"((unsigned short)run) : "memory");
+            run += h[b];
         }
-        __syncwarp();
-        /* stable scatter: two chunks of 32 per iteration so that two MATCH are in flight */
-        for (int i = lane; i < sm.Spad; i += 64) {
-            uint32_t k[2], d[2]; unsigned short p[2]; unsigned peers[2]; bool ok[2];
+        if (lane == 31) asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.M + 2 * 256), "h"((unsigned short)run) : "memory");
+    }
+    /* ---- saturation bins: the bin of edge d that holds its decorrelated syndrome number n_cv-1+3d, and how many lie below ---- */
+    for (int p = 0; 2 * p < dc; p++) {
+        uint32_t h[8], tot = 0;                                                  /* packed: edge 2p in the low half, 2p+1 in the high half */
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int ii = i + 32 * u;
-                ok[u] = ii < sm.Spad;
-                k[u] = ok[u] ? lds_u32(sm.key[src] + 4 * ii) : 0xffffffffu;
-                p[u] = 0xffff;
-                if (ok[u]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p[u]) : "r"(sm.pay[src] + 2 * ii));
-                d[u] = pass < 4 ? ((k[u] >> shift) & 255u) : (ok[u] ? synd_symbol_digit(sm, src, ii) : 255u);
-            }
+        for (int b = 0; b < 8; b++) { h[b] = lds_u32(sm.hsat + 1024 * p + 4 * (lane * 8 + b)); tot += h[b]; }
+        uint32_t inc = tot;
 #pragma unroll
-            for (int u = 0; u < 2; u++) peers[u] = __match_any_sync(NB_FULL, d[u]);
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(NB_FULL, inc, o); if (lane >= o) inc += t; }
+        uint32_t run = inc - tot;
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                if (i - lane + 32 * u < sm.Spad) {          /* warp-uniform */
-                    const uint32_t base = lds_u32(sm.hist + 4 * d[u]);
-                    const uint32_t pos = base + __popc(peers[u] & lt);
-                    sts_u32(sm.key[dst] + 4 * pos, k[u]);
-                    asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.pay[dst] + 2 * pos), "h"(p[u]) : "memory");
-                    __syncwarp();
-                    if ((peers[u] & lt) == 0) sts_u32(sm.hist + 4 * d[u], base + __popc(peers[u]));
-                    __syncwarp();
+        for (int b = 0; b < 8; b++) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int d = 2 * p + s, target = sm.n_cv - 1 + 3 * d;
+                const int below = (int)((run >> (16 * s)) & 0xffffu), here = (int)((h[b] >> (16 * s)) & 0xffffu);
+                if (d < dc && below <= target && target < below + here) {
+                    sts_u32(sm.perm + 128 + 4 * d, (uint32_t)(lane * 8 + b));
+                    sts_u32(sm.perm + 192 + 4 * d, (uint32_t)below);
                 }
+            }
+            run += h[b];
+        }
+    }
+    __syncwarp();
+    /* ---- scatter into the symbol groups (any order inside a group) + candidates of the saturation bins ---- */
+    {
+        /* the four (eight) saturation bins packed into one (two) words: a candidate test is a byte compare */
+        uint32_t sb0 = 0, sb1 = 0;
+        for (int d = 0; d < dc; d++) {
+            const uint32_t b = lds_u32(sm.perm + 128 + 4 * d) & 255u;
+            if (d < 4) sb0 |= b << (8 * d); else sb1 |= b << (8 * (d - 4));
+        }
+        __syncwarp();                                    /* the saturation histograms are about to be overwritten by the grouped keys */
+#pragma unroll 2
+        for (int i = lane; i < S; i += 32) {
+            const uint32_t key = lds_u32(sm.keya + 4 * i), gf = lds_u8(sm.gfa + i), mem = lds_u8(sm.cfgmask + i);
+            uint32_t pos;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(sm.hist + 4 * gf) : "memory");
+            sts_u32(sm.gkey + 4 * pos, key);
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * pos), "h"((unsigned short)i) : "memory");
+            const uint32_t bin4 = synd_bin(key) * 0x01010101u;
+            /* byte d of eq is 0xff where the syndrome's bin is edge d's saturation bin */
+            uint32_t hit = (__vcmpeq4(bin4, sb0) & 0x08040201u);
+            hit = (hit | (hit >> 8) | (hit >> 16) | (hit >> 24)) & 15u;
+            if (dc > 4) { uint32_t h2 = __vcmpeq4(bin4, sb1) & 0x08040201u; h2 = (h2 | (h2 >> 8) | (h2 >> 16) | (h2 >> 24)) & 15u; hit |= h2 << 4; }
+            hit &= mem;
+            while (hit) {                                /* rare: a few syndromes per edge share the bin */
+                const int d = __ffs(hit) - 1;
+                hit &= hit - 1u;
+                uint32_t cpos;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(cpos) : "r"(sm.perm + 256 + 4 * d) : "memory");
+                if (cpos < NB_SYND_CAND) sts_u32(sm.cand + 4 * (d * NB_SYND_CAND + cpos), key);
             }
         }
     }
-}
-
-/* Branch-free bayes(): every lane of the walk below evaluates it on every hit, so divergence would cost more than the
- * few extra instructions (same operations and roundings as synd_bayes). */
-__device__ __forceinline__ float synd_bayes_sel(float m1, float m2)
-{
-    const float mn = fminf(m1, m2), hi = fmaxf(m1, m2);          /* M1 < M2 ? (M1, M2) : (M2, M1); equal values give the same pair */
-    const float dif = __double2float_rn(__dsub_rn((double)hi, (double)mn));
-    const float f = dif < 0.1f ? 0.5f : dif < 0.2f ? 0.75f : dif < 2.0f ? 0.9375f : 1.0f;
-    const float a = __fmul_rn(f, mn);
-    const float b = __double2float_rn(__dmul_rn(0.825, (double)mn));
-    return (dif >= 0.2f && dif < 1.0f) ? b : a;
-}
-
-/* step 4, saturation levels: sat_d = LLR of decorrelated syndrome number n_cv-1+3d in the sorted order (:195), for every
- * presorted position d; stored as f32 at sm.perm + 64 + 4d.  Must run before synd_walk overwrites the sorted buffer. */
-__device__ __forceinline__ void synd_sats(const SyndMem &sm, int lane)
-{
-    const int dc = sm.dc;
-    const unsigned lt = (1u << lane) - 1u;
+    __syncwarp();
+    /* ---- saturation levels (:195): exact order statistic among the candidates of the bin ---- */
     for (int d = 0; d < dc; d++) {
-        const int target = sm.n_cv - 1 + 3 * d;
-        float sat = 0.0f;
-        int cnt = 0;
-        for (int i = lane; i < sm.Spad; i += 32) {
-            unsigned short p;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.pay[0] + 2 * i));
-            const bool keep = (int)p < sm.S && lds_u8(sm.cfg + (int)p * dc + d) == 0;         /* :96-98 */
-            const unsigned bal = __ballot_sync(NB_FULL, keep);
-            const int n = __popc(bal);
-            if (cnt + n > target) {
-                const bool mine = keep && cnt + __popc(bal & lt) == target;
-                const unsigned who = __ballot_sync(NB_FULL, mine);
-                sat = __shfl_sync(NB_FULL, __uint_as_float(lds_u32(sm.key[0] + 4 * i)), __ffs(who) - 1);
-                break;
+        const int m = (int)lds_u32(sm.perm + 256 + 4 * d);
+        const int want = sm.n_cv - 1 + 3 * d - (int)lds_u32(sm.perm + 192 + 4 * d);      /* rank inside the bin */
+        if (m <= NB_SYND_CAND) {
+            for (int u = 0; 32 * u < m; u++) {
+                const int ci = lane + 32 * u;
+                const uint32_t c = ci < m ? lds_u32(sm.cand + 4 * (d * NB_SYND_CAND + ci)) : 0xffffffffu;
+                int lt = 0, le = 0;
+                for (int j = 0; j < m; j++) {
+                    const uint32_t x = lds_u32(sm.cand + 4 * (d * NB_SYND_CAND + j));
+                    lt += x < c; le += x <= c;
+                }
+                if (ci < m && lt <= want && want < le) sts_u32(sm.perm + 64 + 4 * d, c);   /* equal candidates write the same value */
             }
-            cnt += n;
+        } else {
+            /* more syndromes in one bin than the buffer holds (e.g. many equal LLRs): the k-th smallest bit pattern among the
+             * edge's decorrelated syndromes by a bitwise search, counts over the warp */
+            const int target = sm.n_cv - 1 + 3 * d;
+            uint32_t prefix = 0;
+            for (int bit = 31; bit >= 0; bit--) {
+                const uint32_t cand = prefix | (1u << bit), himask = ~((1u << bit) - 1u);
+                int cnt = 0;                                                              /* syndromes whose bits above 'bit' are below cand's */
+                for (int i = lane; i < S; i += 32)
+                    cnt += ((lds_u8(sm.cfgmask + i) >> d) & 1u) && ((lds_u32(sm.keya + 4 * i) & himask) < cand);
+                cnt = __reduce_add_sync(NB_FULL, cnt);
+                if (cnt <= target) prefix = cand;                                         /* the k-th value has this bit set */
+            }
+            if (lane == 0) sts_u32(sm.perm + 64 + 4 * d, prefix);
         }
-        if (lane == 0) sts_f32(sm.perm + 64 + 4 * d, sat);
+    }
+    __syncwarp();
+    /* ---- order every symbol group by (LLR, configuration): every lane a run of whole groups of about S/32 entries ---- */
+    {
+        const int gfirst = synd_lane_group(sm, lane);
+        int glast = __shfl_down_sync(NB_FULL, gfirst, 1);
+        if (lane == 31) glast = 256;
+        int ge = (int)synd_M(sm, (uint32_t)gfirst);
+#pragma unroll 1
+        for (int g = gfirst; g < glast; g++) {
+            const int gs = ge;
+            ge = (int)synd_M(sm, (uint32_t)(g + 1));
+            for (int i = gs + 1; i < ge; i++) {
+                const uint32_t k = lds_u32(sm.gkey + 4 * i);
+                unsigned short p;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.gpay + 2 * i));
+                int j = i - 1;
+                while (j >= gs) {
+                    const uint32_t kj = lds_u32(sm.gkey + 4 * j);
+                    unsigned short pj;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pj) : "r"(sm.gpay + 2 * j));
+                    if (!(kj > k || (kj == k && pj > p))) break;
+                    sts_u32(sm.gkey + 4 * (j + 1), kj);
+                    asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * (j + 1)), "h"(pj) : "memory");
+                    j--;
+                }
+                sts_u32(sm.gkey + 4 * (j + 1), k);
+                asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * (j + 1)), "h"(p) : "memory");
+            }
+        }
     }
     __syncwarp();
 }
 
-/* step 4 for the presorted positions d0 .. d0+nd-1 (nd <= 4) in ONE walk: on return out_k[256] = sm.key[0] + 1024 k
+/* step 4 for the presorted positions d0 .. d0+nd-1 (nd <= 4) in ONE walk: on return out_k[256] = sm.rows + 1024 k
  * (f32, indexed by the binary image of the rotated symbol) holds M_CtoV_LLR[d0+k][.] after saturation
  * (syndrome_decoder.c:93-209).  The reference walks the sorted syndromes and, per symbol, lets the first hit set the LLR
- * and every later hit go through bayes(); hits of different symbols do not interact, so lane L replays the syndromes of
- * the symbol groups 8L..8L+7 (one contiguous range of the symbol-grouped order, ascending inside a group) for all nd
- * edges at once and scatters the results to the symbols (group ^ best symbol of the edge). */
+ * and every later hit go through bayes(); hits of different symbols do not interact, so every lane replays the syndromes of
+ * its run of symbol groups (contiguous in the symbol-grouped order, ascending inside a group) for all nd edges at once and
+ * scatters the results to the symbols (group ^ best symbol of the edge). */
 __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, float offset, int lane)
 {
-    const int dc = sm.dc;
     uint32_t x[4]; float sat[4], hi[4], m[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -252,48 +333,38 @@ __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, flo
         hi[k] = __fadd_rn(sat[k], offset);
         m[k] = 0.0f;
     }
+    const int gfirst = synd_lane_group(sm, lane);
+    int glast = __shfl_down_sync(NB_FULL, gfirst, 1);
+    if (lane == 31) glast = 256;
+    const int lo = (int)synd_M(sm, (uint32_t)gfirst), hi_i = (int)synd_M(sm, (uint32_t)glast);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 4; k++)                                  /* symbols without a hit keep the initial 1500.0 (:131), which the saturation (:198-209) turns into sat + offset unless sat >= 1500 */
         if (k < nd) {
-            const uint32_t a = sm.key[0] + 1024 * k + lane * 32;
+            const uint32_t a = sm.rows + 1024 * k + lane * 16;
             const float unset = 1500.0f > sat[k] ? hi[k] : 1500.0f;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+16], {%1, %1, %1, %1};" :: "r"(a), "f"(unset) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+512], {%1, %1, %1, %1};" :: "r"(a), "f"(unset) : "memory");
         }
     __syncwarp();
-    const uint32_t g0 = (uint32_t)lane * 8u;
-    const int lo = (int)lds_u32(sm.M + 4 * g0);
-    const int hi_i = g0 + 8u >= 256u ? sm.Spad : (int)lds_u32(sm.M + 4 * (g0 + 8u));
-    uint32_t cur = 0xffffffffu, have = 0u;
-    for (int i = lo; i <= hi_i; i++) {                           /* one extra trip flushes the last group */
-        uint32_t p = 0xffffu, g = 0xfffffffeu, cw = 0xffffffffu;
-        float llr = 0.0f;
-        if (i < hi_i) {
-            unsigned short ps;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ps) : "r"(sm.pay[1] + 2 * i));
-            p = ps;
-            if ((int)p >= sm.S) continue;                        /* padding (tail of group 255) */
-            g = lds_u8(sm.gf + p);
-            llr = __uint_as_float(lds_u32(sm.key[1] + 4 * i));
-            if (dc == 4) cw = lds_u32(sm.cfg + 4 * p);
-            else {
-                cw = 0u;
-#pragma unroll
-                for (int k = 0; k < 4; k++) cw |= (k < nd ? lds_u8(sm.cfg + p * dc + d0 + k) : 1u) << (8 * k);
-            }
-        }
-        if (g != cur) {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if ((have >> k) & 1u) sts_f32(sm.key[0] + 1024 * k + 4 * ((cur ^ x[k]) & 255u), m[k] > sat[k] ? hi[k] : m[k]);
-            cur = g; have = 0u;
-        }
+    const uint32_t ndmask = (1u << nd) - 1u;
+    uint32_t have = 0u, gcur = (uint32_t)gfirst;
+    int gend = (int)synd_M(sm, gcur + 1u);                       /* end of group gcur in the grouped order */
+    for (int i = lo; i < hi_i; i++) {
+        while (i >= gend) { gcur++; gend = (int)synd_M(sm, gcur + 1u); }    /* empty groups are skipped; i < M[glast] bounds gcur */
+        unsigned short ps;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ps) : "r"(sm.gpay + 2 * i));
+        const float llr = __uint_as_float(lds_u32(sm.gkey + 4 * i));
+        const uint32_t mem = (lds_u8(sm.cfgmask + (uint32_t)ps) >> d0) & ndmask;       /* decorrelation, :96-98 */
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (k < nd && ((cw >> (8 * k)) & 255u) == 0u) {      /* decorrelation, :96-98 */
-                m[k] = ((have >> k) & 1u) ? synd_bayes_sel(llr, m[k]) : llr;
-                have |= 1u << k;
-            }
+            if ((mem >> k) & 1u) m[k] = ((have >> k) & 1u) ? synd_bayes_sel(llr, m[k]) : llr;
+        }
+        have |= mem;
+        if (i + 1 == gend) {                                     /* last syndrome of the symbol: saturation (:198-209) and store */
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((have >> k) & 1u) sts_f32(sm.rows + 1024 * k + 4 * ((gcur ^ x[k]) & 255u), m[k] > sat[k] ? hi[k] : m[k]);
+            have = 0u;
         }
     }
     __syncwarp();

@@ -470,6 +470,59 @@ def test_full_size_multi_wave_batch_spot_checked_against_oracle():
     o.close(); d.close()
 
 
+def _multi_wave_case(rel, n_m, ebn, ecn, frames_checked, state_frames=2, fpc=1):
+    """A batch of at least four waves of the persistent grid through the chunked end-to-end path at a benched operating
+    point; `frames_checked` frames compared with the oracle (decisions, syndrome, iterations), the last `state_frames` of
+    them -- they sit in the last wave, so their slots still hold their state -- also on every APP and CtoV bit."""
+    code = nbldpc.Code(matrix_path(rel))
+    o = ol.Oracle(matrix_path(rel), code.dialect)
+    kw, okw = {}, {}
+    if ecn:
+        cfg = o.build_config_table(int(code.row_deg[0]), min(19, n_m - 1), 15, 5, 1000)
+        kw = dict(ecn_kind=1, d1=min(19, n_m - 1), d2=15, d3=5, cfg_trunc=1000, n_cv=25)
+        okw = dict(ecn=1, cfg=cfg, n_cv=25)
+    d = nbldpc.Decoder(code, n_m, 25, 10, 0.3, max_batch=4096, frames_per_cta=fpc, **kw)     # enough groups to fill the persistent grid
+    geo = d.geometry()
+    d.close()
+    wave = geo["grid"] * geo["frames_per_cta"]
+    B = 4 * wave + 17
+    d = nbldpc.Decoder(code, n_m, 25, 10, 0.3, max_batch=B, frames_per_cta=fpc, **kw)
+    assert d.geometry()["grid"] * d.geometry()["frames_per_cta"] == wave and B > 4 * wave, "the batch must span more than four waves of the grid"
+    fr, sigma = product_frames(code, 6, ebn)
+    rng = np.random.default_rng(11 + ecn)
+    pick = rng.integers(0, 6, B)
+    noisy = np.stack([f["noisy"] for f in fr])[pick]
+    noisy = noisy + (rng.standard_normal(noisy.shape) * 0.02).astype(np.float32)       # every frame differs
+    dec, synd, it = d.decode_noisy(noisy, sigma)
+    frames = [0, wave, B // 2] + list(range(B - max(frames_checked - 3, state_frames), B))
+    for f in frames:
+        want_state = f >= B - state_frames
+        r = o.decode_frame(o.channel_llr(noisy[f], sigma), n_m, 25, 10, 0.3, want_state=want_state, **okw)
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"] and it[f] == r["iters"], (rel, f)
+        if want_state:
+            app, ctov = d.get_state(f)
+            assert app.tobytes() == r["app"].tobytes(), "APP bits of frame %d differ" % f
+            assert ctov.tobytes() == r["ctov"].tobytes(), "CtoV bits of frame %d differ" % f
+    o.close(); d.close()
+    return it
+
+
+def test_config5_syndrome_multi_wave_against_oracle():
+    """BASELINE config 5 as written (syndrome_decoder path) at the bench's operating point, Eb/N0 2.0 dB"""
+    _multi_wave_case("matrices/AD_64800_R12_GF256", 20, 2.0, 1, frames_checked=5, state_frames=1)
+
+
+def test_config3_multi_wave_against_oracle_never_converges():
+    """BASELINE config 3 at 1.2 dB: no frame converges, every check node of every pass is compared through the final state"""
+    it = _multi_wave_case("matrices/MatDeclercq_R12_GF64", 20, 1.2, 0, frames_checked=6, state_frames=2, fpc=2)
+    assert (it == 10).mean() > 0.9
+
+
+def test_config4_multi_wave_against_oracle_short_lists():
+    """BASELINE config 4 (GF(16), dc = 8) at 3.0 dB: 12.5 % of the check-to-variable rows carry fewer than n_m - 1 pairs"""
+    _multi_wave_case("matrices/Ahmed_64800_R34_GF16", 16, 3.0, 0, frames_checked=6, state_frames=2)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Monte-Carlo statistics: the C driver (csrc/nbldpc_mc.c) and the sharded loop (multigpu.py) against the stock binary
 # ---------------------------------------------------------------------------------------------------
@@ -551,6 +604,33 @@ def test_c_driver_stops_at_the_40th_erroneous_frame_in_frame_order(tmp_path):
         mf = re.search(r"FER=\s*(\d+)\s*/\s*(\d+)", line)
         assert (int(mf.group(1)), int(mf.group(2))) == (40, int(m[-1][2])), line            # results file: nb = frame of the 40th error
     assert outs[0] == outs[1] == outs[2], outs
+
+
+def test_reference_main_with_gpu_check_node(tmp_path):
+    """The compiled drop-in (boundary 1, include/bubble_decoder.h:17): oracle/_ref/essai_gpucn is the reference's unmodified
+    main() built with -DCheckPassLogEMS=nbgpu_CheckPassLogEMS and linked against libnbldpc_b200.so through the maintainer-side
+    binding csrc/nbgpu_bind.c (nbgpu_bind_code on the reference's own code_t / table_t).  Its console must equal the stock
+    binary's on the reference's own small case."""
+    import re
+    import subprocess
+    gpucn, stock = os.path.join(ol.REF_DIR, "essai_gpucn"), os.path.join(ol.REF_DIR, "essai_ubs")
+    if not (os.path.exists(gpucn) and os.path.exists(stock)):
+        pytest.skip("oracle/_ref/essai_gpucn not available (build oracle/_ref where /root/reference exists)")
+    args = ["2000", "10", "matrices/N96_K48_GF64", "3.0", "20", "0.3", "25"]
+    outs = []
+    for exe in (gpucn, stock):
+        d = tmp_path / os.path.basename(exe)
+        os.makedirs(d / "data")
+        os.symlink(os.path.join(ol.REF_DIR, "matrices"), d / "matrices")
+        r = subprocess.run([exe] + args, cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:]
+        m = re.findall(r"<(\d+)> FER=\s*(\d+)\s*/\s*(\d+)\s*=\s*[\d.]+\s*BER=\s*(\d+)\s*/\s*x\s*=\s*[\d.eE+-]+\s*avr_it=([\d.]+)", r.stdout)
+        assert m, r.stdout[-2000:]
+        outs.append(m[-1])
+        res = list((d / "data").glob("results_*.txt"))[0].read_text().split("time:")[0]
+        outs.append(res)
+    assert outs[0] == outs[2] == ("0", "24", "2000", "153", "1.56"), outs
+    assert outs[1] == outs[3], outs                       # the results-file line up to the time stamp
 
 
 def test_sharded_monte_carlo_on_the_gpu():
