@@ -278,10 +278,25 @@ def synth_frames(code, B, ebn, seed, pool=8):
 
 
 def git_head():
+    """Commit of the tree when .git is there; on the GPU box (a snapshot without history) a hash of the kernel sources,
+    so that a traffic capture can still be tied to the code it measured."""
     try:
-        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True).stdout.strip() or None
+        h = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True).stdout.strip()
+        if h:
+            return h
     except OSError:
-        return None
+        pass
+    return "src-" + source_id()
+
+
+def source_id():
+    import glob
+    import hashlib
+    m = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, "ems-decoder-of-nb-ldpc-codes_b200", "csrc", "*.[ch]*")) +
+                    glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        m.update(open(f, "rb").read())
+    return m.hexdigest()[:12]
 
 
 def measured_traffic(wl, ecn, B, kernel_ms):
@@ -295,7 +310,8 @@ def measured_traffic(wl, ecn, B, kernel_ms):
     if tj.get("frames") != B or tj.get("ecn") != ecn or not tj.get("kernel_ms"):
         return None, {"capture": os.path.basename(tp), "rejected": "other launch size or check node"}
     dev = abs(tj["kernel_ms"] - kernel_ms) / kernel_ms
-    info = {"capture": os.path.basename(tp), "git": tj.get("git"), "kernel_ms_at_capture": tj["kernel_ms"], "kernel_ms_deviation": dev}
+    info = {"capture": os.path.basename(tp), "git": tj.get("git"), "source_id": tj.get("source_id"), "source_id_now": source_id(),
+            "kernel_ms_at_capture": tj["kernel_ms"], "kernel_ms_deviation": dev}
     if dev > 0.03:
         info["rejected"] = "kernel duration differs by more than 3 % from the live measurement: capture is stale"
         return None, info
@@ -484,7 +500,7 @@ def ours(args, rank, local_rank, world):
         line = {"metric": "decoded info Mbit/s at fixed iterations (%d passes)" % passes, "value": head["value"], "unit": "Mbit/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic (encoder codewords + numpy Gaussian noise at the reference's sigma)",
-                "git": git_head()}
+                "git": git_head(), "source_id": source_id()}
         for k in ("frames_per_s", "config", "geometry", "e2e", "gpu_launches", "roofline", "clocks", "simulation", "counters", "sharding_check"):
             if k in head:
                 line[k] = head[k]

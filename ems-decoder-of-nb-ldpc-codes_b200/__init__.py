@@ -54,6 +54,17 @@ def build(force=False):
 _lib = None
 
 
+def apsk64_table():
+    """The normalised 64-APSK constellation of ModelChannel_AWGN_64 (channel.c:133-222), [64][2], by binary image."""
+    mod = np.zeros((64, 2), np.float32)
+    _check(lib().nbgpu_apsk64_table(mod.ctypes.data_as(_fp)))
+    return mod
+
+
+def sigma_apsk64(ebn):
+    return float(lib().nbgpu_sigma_apsk64(C.c_float(ebn)))
+
+
 def lib():
     """The loaded C-ABI library.  Fails loudly when it has not been built."""
     global _lib
@@ -79,6 +90,12 @@ def lib():
         "nbgpu_random_codeword": (C.c_int, [vp, C.POINTER(Rng), _ip, _ip]),
         "nbgpu_sigma": (C.c_float, [vp, C.c_float]),
         "nbgpu_awgn_bpsk_noise": (C.c_int, [vp, C.POINTER(Rng), _ip, C.c_float, _fp]),
+        "nbgpu_apsk64_table": (C.c_int, [_fp]),
+        "nbgpu_sigma_apsk64": (C.c_float, [C.c_float]),
+        "nbgpu_awgn_apsk64_noise": (C.c_int, [vp, C.POINTER(Rng), _ip, C.c_float, _fp]),
+        "nbgpu_channel_awgn_apsk64": (C.c_int, [vp, _fp, C.c_float, C.c_int, _fp, _fp, _ip]),
+        "nbgpu_decode_apsk64": (C.c_int, [vp, _fp, C.c_float, C.c_int, _ip, _ip, _ip]),
+        "nbgpu_upload_apsk64": (C.c_int, [vp, _fp, C.c_float, C.c_int]),
         "nbgpu_create": (C.c_int, [C.POINTER(vp), vp, C.POINTER(Params), C.c_int, C.c_int]),
         "nbgpu_destroy": (None, [vp]),
         "nbgpu_last_error": (C.c_char_p, [vp]),
@@ -202,6 +219,13 @@ class Code:
         _check(lib().nbgpu_awgn_bpsk_noise(self.h, C.byref(self.rng), _i(nb), C.c_float(ebn), _f(noisy)))
         return noisy
 
+    def noise_apsk64(self, nbin, ebn):
+        """channel.c:234-263 for one frame of a GF(64) code sent as 64-APSK symbols: noisy[N][2]."""
+        noisy = np.zeros((self.N, 2), np.float32)
+        nb = np.ascontiguousarray(nbin, np.int32) if nbin is not None else None
+        _check(lib().nbgpu_awgn_apsk64_noise(self.h, C.byref(self.rng), _i(nb), C.c_float(ebn), _f(noisy)))
+        return noisy
+
     def accumulate_stats(self, codeword_bits, decide, synd, iters, stats):
         cb = np.ascontiguousarray(codeword_bits, np.int32)
         d = np.ascontiguousarray(decide, np.int32)
@@ -247,6 +271,24 @@ class Decoder:
         _check(lib().nbgpu_decode_noisy(self.h, _f(noisy), C.c_float(sigma), B, _i(d), _i(s), _i(it)), self.h)
         self.B = B
         return d, s, it
+
+    def decode_apsk64(self, noisy, sigma):
+        """nbgpu_decode_apsk64: frames of a GF(64) code received as 64-APSK samples [B, N, 2]."""
+        noisy = np.ascontiguousarray(noisy, np.float32).reshape(-1, self.code.N, 2)
+        B = noisy.shape[0]
+        d, s, it = self._out(B)
+        _check(lib().nbgpu_decode_apsk64(self.h, _f(noisy), C.c_float(sigma), B, _i(d), _i(s), _i(it)), self.h)
+        self.B = B
+        return d, s, it
+
+    def channel_apsk64(self, noisy, sigma, want_sorted=False):
+        noisy = np.ascontiguousarray(noisy, np.float32).reshape(-1, self.code.N, 2)
+        B = noisy.shape[0]
+        llr = np.zeros((B, self.code.N, self.code.q), np.float32)
+        il = np.zeros_like(llr) if want_sorted else None
+        ig = np.zeros(llr.shape, np.int32) if want_sorted else None
+        _check(lib().nbgpu_channel_awgn_apsk64(self.h, _f(noisy), C.c_float(sigma), B, _f(llr), _f(il), _i(ig)), self.h)
+        return (llr, il, ig) if want_sorted else llr
 
     def decode_noisy_into(self, noisy, sigma, out):
         """nbgpu_decode_noisy on caller-owned (e.g. pinned) buffers, no allocation: noisy [B,N,logq] f32, out = (decide, synd, iters)."""

@@ -66,7 +66,7 @@ struct KArgs {
     int n_m, nb_oper, passes, early_stop, nb_iter_max;
     float offset;
     int F, nw, cpw, cap, nsteps, L;     /* frames per group, warps per CTA, check nodes per warp, items per step, steps, lists per node */
-    int B, input_kind, frame0;          /* frames of this launch; 0 = noisy samples, 1 = dense LLR; batch index of its first frame */
+    int B, input_kind, frame0;          /* frames of this launch; 0 = BPSK samples, 1 = dense LLR, 2 = 64-APSK samples; batch index of its first frame */
     double den;                         /* 2.0 * (double)(float)(sigma*sigma), channel.c:73 */
     const int *step_ptr, *isolated;
     int n_isolated;
@@ -74,6 +74,7 @@ struct KArgs {
     const uint32_t *einfo;              /* [E] variable | coefficient << 20 | last-visit flag << 28 */
     const int *row_ptr, *col;
     const uint8_t *hval, *rotin, *rotout, *img, *inv;
+    const float *mod;                   /* [64][2] normalised 64-APSK constellation by binary image (GF(64) only), input_kind 2 */
     int gf_closed;
     const float *in;
     float *app; uint8_t *ctov; uint8_t *dec;
@@ -263,6 +264,23 @@ __device__ __forceinline__ void intake_variable(const float *noisy_n, double den
 #pragma unroll
     for (int j = 0; j < VPL; j++) v[j] = (Q >= 32 || lane < Q) ? row[img[QTraits<Q>::sym(lane, j)]] : 0.0f;
     __syncwarp();
+}
+
+/* LLR intake for one variable of a GF(64) code sent as one 64-APSK symbol (channel.c:268-291): for every symbol k,
+ * TMP[k] = (float)( (double)((I - mI)^2) / (2 sigma^2) + (double)((Q - mQ)^2) / (2 sigma^2) ) with (mI, mQ) the constellation point of the
+ * symbol's binary image; differences and squares in f32, divisions and the sum in f64, as the reference evaluates them. */
+template <int Q>
+__device__ __forceinline__ void intake_apsk64(const float *noisy_n, double den, const float *mod, const uint8_t *img, int lane,
+                                              float (&v)[QTraits<Q>::VPL])
+{
+    const float y0 = noisy_n[0], y1 = noisy_n[1];
+#pragma unroll
+    for (int j = 0; j < QTraits<Q>::VPL; j++) {
+        const int som = img[QTraits<Q>::sym(lane, j) & 63];
+        const float d0 = __fsub_rn(y0, mod[2 * som]), d1 = __fsub_rn(y1, mod[2 * som + 1]);
+        const double a = __ddiv_rn((double)__fmul_rn(d0, d0), den), b = __ddiv_rn((double)__fmul_rn(d1, d1), den);
+        v[j] = __double2float_rn(__dadd_rn(a, b));
+    }
 }
 
 __device__ __forceinline__ void load_gf_tables(unsigned char *smem, const KArgs &a, GFTab &gf)
@@ -643,6 +661,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
             float v[VPL];
             if (a.input_kind == 0) intake_variable<Q>(a.in + ((size_t)(base + f) * N + n) * a.logq, a.den, gf.img, lane,
                                                       reinterpret_cast<double *>(wm.scr[0]), reinterpret_cast<float *>(wm.scr[0]) + 32, v);
+            else if (Q == 64 && a.input_kind == 2) intake_apsk64<Q>(a.in + ((size_t)(base + f) * N + n) * 2, a.den, a.mod, gf.img, lane, v);
             else load_row<Q>(a.in + ((size_t)(base + f) * N + n) * Q, lane, v);
             store_row<Q>(app + ((size_t)f * N + n) * Q, lane, v);
         }
@@ -987,7 +1006,7 @@ __global__ void syndrome_kernel(const KArgs a, const int *decide, int *synd, int
 /* channel intake as a standalone kernel: dense LLR and (optionally) the sorted intrinsic arrays
  * (channel.c:66-91).  The sort is only needed for interface parity with decoder_t.intrinsic_*. */
 template <int Q>
-__global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const float *noisy, float *llr, float *illr, int *igf, int B)
+__global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const float *noisy, float *llr, float *illr, int *igf, int B, int kind)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     constexpr int UW = UNIT_NT / 32;
@@ -997,7 +1016,8 @@ __global__ void __launch_bounds__(UNIT_NT) channel_kernel(const KArgs a, const f
     const long total = (long)B * a.N;
     for (long r = (long)blockIdx.x * UW + warp; r < total; r += (long)gridDim.x * UW) {
         float v[VPL];
-        intake_variable<Q>(noisy + r * a.logq, a.den, a.img, lane, ts[warp], rows[warp], v);
+        if (Q == 64 && kind == 2) intake_apsk64<Q>(noisy + r * 2, a.den, a.mod, a.img, lane, v);
+        else intake_variable<Q>(noisy + r * a.logq, a.den, a.img, lane, ts[warp], rows[warp], v);
         if (llr) store_row<Q>(llr + r * Q, lane, v);
         if (illr) {
             /* full stable sort = q rounds of the exact scan (channel.c:78-91) */
@@ -1053,6 +1073,7 @@ struct nbgpu_ctx {
     uint32_t *d_cninfo, *d_einfo;
     uint8_t *d_cfg; float *d_ctov_dense;
     uint8_t *d_hval, *d_rotin, *d_rotout, *d_img, *d_inv;
+    float *d_mod;
     float *d_app; uint8_t *d_ctov; uint8_t *d_dec;
     float *d_in; size_t in_capacity;
     int *d_decide, *d_synd, *d_iters, *d_frame_slot, *d_slot_frame;
@@ -1325,6 +1346,12 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
         (rc = upload(c, &c->d_rotin, rotin)) || (rc = upload(c, &c->d_rotout, rotout)) ||
         (rc = upload(c, &c->d_img, img)) || (rc = upload(c, &c->d_inv, inv))) { nbgpu_destroy(c); return rc; }
     if (p->ecn_kind == 1) { if ((rc = upload(c, &c->d_cfg, cfg8))) { nbgpu_destroy(c); return rc; } k.cfg = c->d_cfg; }
+    if (q == 64) {                                       /* 64-APSK intake (ModelChannel_AWGN_64): the constellation, built on the host */
+        std::vector<float> mod(128);
+        nbgpu_apsk64_table(mod.data());
+        if ((rc = upload(c, &c->d_mod, mod))) { nbgpu_destroy(c); return rc; }
+        k.mod = c->d_mod;
+    }
     k.row_ptr = c->d_row_ptr; k.col = c->d_col; k.cninfo = c->d_cninfo; k.einfo = c->d_einfo; k.step_ptr = c->d_step_ptr; k.isolated = c->d_isolated;
     k.hval = c->d_hval; k.rotin = c->d_rotin; k.rotout = c->d_rotout; k.img = c->d_img; k.inv = c->d_inv;
 
@@ -1374,7 +1401,7 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     void *bufs[] = { c->d_cfg, c->d_ctov_dense, c->d_row_ptr, c->d_col, c->d_cninfo, c->d_einfo, c->d_step_ptr, c->d_isolated, c->d_hval, c->d_rotin,
-                     c->d_rotout, c->d_img, c->d_inv, c->d_app, c->d_ctov, c->d_dec, c->d_in, c->d_decide, c->d_synd,
+                     c->d_rotout, c->d_img, c->d_inv, c->d_mod, c->d_app, c->d_ctov, c->d_dec, c->d_in, c->d_decide, c->d_synd,
                      c->d_iters, c->d_frame_slot, c->d_slot_frame, c->d_queue };
     for (void *b : bufs) if (b) cudaFree(b);
     source_teardown(c);
@@ -1421,6 +1448,19 @@ extern "C" int nbgpu_upload_llr(nbgpu_ctx *c, const float *llr, int B)
 {
     if (!c) return NBGPU_EINVAL;
     return upload_common(c, llr, (size_t)c->N * c->q, B, 1);
+}
+static int apsk64_ok(nbgpu_ctx *c)
+{
+    if (c->q == 64) return 1;
+    ctx_err(c, "64-APSK intake (ModelChannel_AWGN_64, channel.c:112) maps one GF(64) symbol to one constellation point: q = %d", c->q);
+    return 0;
+}
+extern "C" int nbgpu_upload_apsk64(nbgpu_ctx *c, const float *noisy, float sigma, int B)
+{
+    if (!c) return NBGPU_EINVAL;
+    if (!apsk64_ok(c)) return NBGPU_EINVAL;
+    c->k.den = 2.0 * (double)(float)(sigma * sigma);                      /* 2.0*SQR(sigma), channel.c:280 */
+    return upload_common(c, noisy, (size_t)c->N * 2, B, 2);
 }
 
 extern "C" int nbgpu_run(nbgpu_ctx *c)
@@ -1581,6 +1621,13 @@ extern "C" int nbgpu_decode_llr(nbgpu_ctx *c, const float *llr, int B, int *deci
 {
     if (!c) return NBGPU_EINVAL;
     return decode_host(c, llr, (size_t)c->N * c->q, 1, B, decide, synd, iters);
+}
+extern "C" int nbgpu_decode_apsk64(nbgpu_ctx *c, const float *noisy, float sigma, int B, int *decide, int *synd, int *iters)
+{
+    if (!c) return NBGPU_EINVAL;
+    if (!apsk64_ok(c)) return NBGPU_EINVAL;
+    c->k.den = 2.0 * (double)(float)(sigma * sigma);                      /* 2.0*SQR(sigma), channel.c:280 */
+    return decode_host(c, noisy, (size_t)c->N * 2, 2, B, decide, synd, iters);
 }
 
 
@@ -1923,21 +1970,21 @@ extern "C" int nbgpu_decision_syndrome(nbgpu_ctx *c, const float *app, int *deci
     return NBGPU_OK;
 }
 
-extern "C" int nbgpu_channel_awgn_bpsk(nbgpu_ctx *c, const float *noisy, float sigma, int B, float *llr, float *illr, int *igf)
+static int channel_common(nbgpu_ctx *c, const float *noisy, float sigma, int B, float *llr, float *illr, int *igf, int kind)
 {
-    if (!c || !noisy || B < 1 || ((illr == NULL) != (igf == NULL))) { ctx_err(c, "nbgpu_channel_awgn_bpsk: bad argument"); return NBGPU_EINVAL; }
+    if (!c || !noisy || B < 1 || ((illr == NULL) != (igf == NULL))) { ctx_err(c, "nbgpu_channel_awgn_*: bad argument"); return NBGPU_EINVAL; }
     CK(c, cudaSetDevice(c->device));
-    const int N = c->N, q = c->q;
+    const int N = c->N, q = c->q, per = kind == 2 ? 2 : c->logq;
     DevBuf<float> dn, dl, dil; DevBuf<int> dig;
-    CK(c, dn.alloc((size_t)B * N * c->logq)); CK(c, dl.alloc((size_t)B * N * q));
+    CK(c, dn.alloc((size_t)B * N * per)); CK(c, dl.alloc((size_t)B * N * q));
     if (illr) { CK(c, dil.alloc((size_t)B * N * q)); CK(c, dig.alloc((size_t)B * N * q)); }
-    CK(c, cudaMemcpyAsync(dn.p, noisy, (size_t)B * N * c->logq * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(dn.p, noisy, (size_t)B * N * per * 4, cudaMemcpyHostToDevice, c->stream));
     KArgs k = c->k;
     k.den = 2.0 * (double)(float)(sigma * sigma);
     const int grid = (int)std::min<long>(((long)B * N + UNIT_NT / 32 - 1) / (UNIT_NT / 32), 148 * 8);
-    if (q == 16) channel_kernel<16><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
-    else if (q == 64) channel_kernel<64><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
-    else channel_kernel<256><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B);
+    if (q == 16) channel_kernel<16><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B, kind);
+    else if (q == 64) channel_kernel<64><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B, kind);
+    else channel_kernel<256><<<grid, UNIT_NT, 0, c->stream>>>(k, dn.p, dl.p, illr ? dil.p : nullptr, illr ? dig.p : nullptr, B, kind);
     CK(c, cudaGetLastError());
     c->launches++;
     CK(c, cudaStreamSynchronize(c->stream));
@@ -1947,4 +1994,14 @@ extern "C" int nbgpu_channel_awgn_bpsk(nbgpu_ctx *c, const float *noisy, float s
         CK(c, cudaMemcpy(igf, dig.p, (size_t)B * N * q * 4, cudaMemcpyDeviceToHost));
     }
     return NBGPU_OK;
+}
+extern "C" int nbgpu_channel_awgn_bpsk(nbgpu_ctx *c, const float *noisy, float sigma, int B, float *llr, float *illr, int *igf)
+{
+    return channel_common(c, noisy, sigma, B, llr, illr, igf, 0);
+}
+extern "C" int nbgpu_channel_awgn_apsk64(nbgpu_ctx *c, const float *noisy, float sigma, int B, float *llr, float *illr, int *igf)
+{
+    if (!c) return NBGPU_EINVAL;
+    if (!apsk64_ok(c)) return NBGPU_EINVAL;
+    return channel_common(c, noisy, sigma, B, llr, illr, igf, 2);
 }

@@ -443,6 +443,62 @@ int nbgpu_awgn_bpsk_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin, fl
     return NBGPU_OK;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * 64-APSK over AWGN (ModelChannel_AWGN_64, channel.c:112-312): one GF(64) symbol = one point of the
+ * DVB-S2X 8+16+20+20 APSK constellation, two noisy reals (I, Q) per symbol.  The host side is the constellation,
+ * sigma and the noise; the LLR computation is a GPU intake kernel (nbldpc_cuda.cu).
+ * ---------------------------------------------------------------------------------------------- */
+#define NB_PI 3.1415926536                                     /* channel.c:18 */
+/* a constellation point as the reference's initialiser writes it (channel.c:133-198): radius * cos / sin(PI * num / den),
+ * evaluated in double, stored as float.  Index = binary image of the symbol (LSB first). */
+#define APSK(r, num, den) { (float)((r) * cos(NB_PI * (num) / (den))), (float)((r) * sin(NB_PI * (num) / (den))) }
+#define APSK1(num, den) { (float)cos(NB_PI * (num) / (den)), (float)sin(NB_PI * (num) / (den)) }
+int nbgpu_apsk64_table(float *mod)
+{
+    /* rings of radius 1, 2.2, 3.6, 5.2 with 8, 16, 20, 20 points; the order is the bit labelling of the constellation */
+    const float pts[64][2] = {
+        APSK(2.2, 25, 16), APSK(2.2, 23, 16), APSK(2.2, 7, 16), APSK(2.2, 9, 16), APSK(5.2, 7, 4), APSK(5.2, 5, 4), APSK(5.2, 1, 4), APSK(5.2, 3, 4),
+        APSK(2.2, 27, 16), APSK(2.2, 21, 16), APSK(2.2, 5, 16), APSK(2.2, 11, 16), APSK(3.6, 7, 4), APSK(3.6, 5, 4), APSK(3.6, 1, 4), APSK(3.6, 3, 4),
+        APSK(5.2, 31, 20), APSK(5.2, 29, 20), APSK(5.2, 9, 20), APSK(5.2, 11, 20), APSK(5.2, 33, 20), APSK(5.2, 27, 20), APSK(5.2, 7, 20), APSK(5.2, 13, 20),
+        APSK(3.6, 31, 20), APSK(3.6, 29, 20), APSK(3.6, 9, 20), APSK(3.6, 11, 20), APSK(3.6, 33, 20), APSK(3.6, 27, 20), APSK(3.6, 7, 20), APSK(3.6, 13, 20),
+        APSK1(13, 8), APSK1(11, 8), APSK1(3, 8), APSK1(5, 8), APSK(5.2, 37, 20), APSK(5.2, 23, 20), APSK(5.2, 3, 20), APSK(5.2, 17, 20),
+        APSK(2.2, 29, 16), APSK(2.2, 19, 16), APSK(2.2, 3, 16), APSK(2.2, 13, 16), APSK(3.6, 37, 20), APSK(3.6, 23, 20), APSK(3.6, 3, 20), APSK(3.6, 17, 20),
+        APSK1(15, 8), APSK1(9, 8), APSK1(1, 8), APSK1(7, 8), APSK(5.2, 39, 20), APSK(5.2, 21, 20), APSK(5.2, 1, 20), APSK(5.2, 19, 20),
+        APSK(2.2, 31, 16), APSK(2.2, 17, 16), APSK(2.2, 1, 16), APSK(2.2, 15, 16), APSK(3.6, 39, 20), APSK(3.6, 21, 20), APSK(3.6, 1, 20), APSK(3.6, 19, 20) };
+    float norm = 0.0f;
+    int i;
+    if (!mod) return NBGPU_EINVAL;
+    for (i = 0; i < 64; i++) norm = pts[i][0] * pts[i][0] + pts[i][1] * pts[i][1] + norm;      /* channel.c:205-211: average power 1 */
+    norm = sqrt(64 / norm);
+    for (i = 0; i < 64; i++) { mod[2 * i] = norm * pts[i][0]; mod[2 * i + 1] = norm * pts[i][1]; }   /* :215-222 */
+    return NBGPU_OK;
+}
+float nbgpu_sigma_apsk64(float EbN)
+{
+    return (float)sqrt(1.0 / (2.0 * pow(10, EbN / 10.0)));      /* channel.c:232 (no code rate here) */
+}
+/* noisy[N][2]: the constellation point of symbol n (binary image nbin[n][0..5], LSB first) plus Box-Muller noise, channel.c:234-263 */
+int nbgpu_awgn_apsk64_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin, float EbN, float *noisy)
+{
+    const double pi = NB_PI;
+    const float sigma = nbgpu_sigma_apsk64(EbN);
+    float mod[128];
+    int n, q;
+    if (!c || !r || !noisy) { nbgpu_set_global_error("nbgpu_awgn_apsk64_noise: NULL argument"); return NBGPU_EINVAL; }
+    if (c->q != 64) { nbgpu_set_global_error("64-APSK maps one GF(64) symbol to one constellation point (q = %d)", c->q); return NBGPU_EINVAL; }
+    nbgpu_apsk64_table(mod);
+    for (n = 0; n < c->N; n++) {
+        int som = 0;
+        for (q = 0; q < 6; q++) som += (nbin ? nbin[n * 6 + q] : 0) << q;
+        for (q = 0; q < 2; q++) {
+            float u = draw_float(r);
+            float v = draw_float(r);
+            noisy[2 * n + q] = mod[2 * som + q] + sigma * sqrt(-2.0 * log(u)) * cos(2.0 * pi * v);
+        }
+    }
+    return NBGPU_OK;
+}
+
 /* NB_LDPC.c:474-507 */
 int nbgpu_accumulate_stats(const nbgpu_code *c, const int *codeword_bits, const int *decide,
                            const int *synd, const int *iters, int B, long *stats)

@@ -78,6 +78,18 @@ float nbgpu_sigma(const nbgpu_code *c, float EbN);                           /* 
 int nbgpu_awgn_bpsk_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin, float EbN,
                           float *noisy /*[N*logq]*/);                        /* channel.c:52-62 */
 
+/* ---- 64-APSK over AWGN: ModelChannel_AWGN_64, channel.c:112-312 (GF(64) codes only) ----
+ * nbgpu_apsk64_table     the normalised DVB-S2X 8+16+20+20 APSK constellation, mod[64][2], indexed by the symbol's binary
+ *                        image (channel.c:133-222)
+ * nbgpu_sigma_apsk64     sigma = sqrt(1 / (2 * 10^(EbN/10))), channel.c:232
+ * nbgpu_awgn_apsk64_noise  noisy[N][2] = constellation point + Box-Muller noise on the caller's drand48 stream, same draw
+ *                        order as the reference (per symbol: u, v for I, then u, v for Q), channel.c:234-263 */
+int nbgpu_apsk64_table(float *mod /*[64][2]*/);
+float nbgpu_sigma_apsk64(float EbN);
+int nbgpu_awgn_apsk64_noise(const nbgpu_code *c, nbgpu_rng *r, const int *nbin /*[N][6] or NULL = all-zero word*/, float EbN,
+                            float *noisy /*[N][2]*/);
+
+
 /* Configuration table of the syndrome-based check node: replaces build_config_table + sort_config_table
  * (syndrome_decoder.c:1542, 2285) and the truncation NB_LDPC.c:198-201.  Returns the number of
  * configurations (rows of dc ints) or a negative error; table may be NULL to query the size. */
@@ -125,10 +137,18 @@ int nbgpu_decode_noisy(nbgpu_ctx *ctx, const float *noisy /*[B][N][logq]*/, floa
                        int *decide, int *synd, int *iters);
 int nbgpu_decode_llr(nbgpu_ctx *ctx, const float *llr /*[B][N][q] GF order*/, int B,
                      int *decide, int *synd, int *iters);
+/* LLR part of ModelChannel_AWGN_64 on the GPU (channel.c:266-308): dense LLR[B][N][64] and, when illr/igf are given, the sorted
+ * intrinsic_LLR / intrinsic_GF; nbgpu_decode_apsk64 = the same intake fused into the decoder (replaces channel.c:266-308 +
+ * NB_LDPC.c:266-474 for B frames); nbgpu_upload_apsk64 + nbgpu_run + nbgpu_download is the resident-input form. */
+int nbgpu_channel_awgn_apsk64(nbgpu_ctx *ctx, const float *noisy /*[B][N][2]*/, float sigma, int B,
+                              float *llr, float *illr, int *igf);
+int nbgpu_decode_apsk64(nbgpu_ctx *ctx, const float *noisy /*[B][N][2]*/, float sigma, int B,
+                        int *decide, int *synd, int *iters);
 
 /* Same work split into stages so that a caller can keep inputs resident in HBM (bench.py "value"):
  * upload (H2D) -> run (kernel only, asynchronous on the ctx stream) -> download (D2H + sync). */
 int nbgpu_upload_noisy(nbgpu_ctx *ctx, const float *noisy, float sigma, int B);
+int nbgpu_upload_apsk64(nbgpu_ctx *ctx, const float *noisy /*[B][N][2]*/, float sigma, int B);   /* 64-APSK samples, see below */
 int nbgpu_upload_llr(nbgpu_ctx *ctx, const float *llr, int B);
 int nbgpu_run(nbgpu_ctx *ctx);                  /* decode the resident batch; returns after launch    */
 int nbgpu_sync(nbgpu_ctx *ctx);

@@ -242,6 +242,69 @@ void nbo_channel_llr(const nbo_code *c, const float *noisy, float sigma, float *
         }
 }
 
+/* ---- 64-APSK channel, ModelChannel_AWGN_64 (channel.c:112-312), GF(64) only ----
+ * Constellation (channel.c:133-198): DVB-S2X 8+16+20+20 APSK.  Restated from its structure: ring radius and angle
+ * PI * num / den per label; the reference's initialiser evaluates radius * cos(...) in double and stores float. */
+static const unsigned char apsk_ring[64] = {   /* 0: r = 1, 1: r = 2.2, 2: r = 3.6, 3: r = 5.2 */
+    1,1,1,1,3,3,3,3, 1,1,1,1,2,2,2,2, 3,3,3,3,3,3,3,3, 2,2,2,2,2,2,2,2,
+    0,0,0,0,3,3,3,3, 1,1,1,1,2,2,2,2, 0,0,0,0,3,3,3,3, 1,1,1,1,2,2,2,2 };
+static const unsigned char apsk_num[64] = {
+    25,23,7,9,7,5,1,3, 27,21,5,11,7,5,1,3, 31,29,9,11,33,27,7,13, 31,29,9,11,33,27,7,13,
+    13,11,3,5,37,23,3,17, 29,19,3,13,37,23,3,17, 15,9,1,7,39,21,1,19, 31,17,1,15,39,21,1,19 };
+static const unsigned char apsk_den[64] = {
+    16,16,16,16,4,4,4,4, 16,16,16,16,4,4,4,4, 20,20,20,20,20,20,20,20, 20,20,20,20,20,20,20,20,
+    8,8,8,8,20,20,20,20, 16,16,16,16,20,20,20,20, 8,8,8,8,20,20,20,20, 16,16,16,16,20,20,20,20 };
+void nbo_apsk64_table(float *mod)
+{
+    static const double radius[4] = { 1.0, 2.2, 3.6, 5.2 };
+    const double PI = 3.1415926536;                                    /* channel.c:18 */
+    float pts[64][2], norm = 0.0f;
+    int i;
+    for (i = 0; i < 64; i++) {
+        const double ang = PI * apsk_num[i] / apsk_den[i];
+        pts[i][0] = (float)(radius[apsk_ring[i]] * cos(ang));
+        pts[i][1] = (float)(radius[apsk_ring[i]] * sin(ang));
+    }
+    for (i = 0; i < 64; i++) norm = pts[i][0] * pts[i][0] + pts[i][1] * pts[i][1] + norm;     /* :205-211 */
+    norm = sqrt(64 / norm);
+    for (i = 0; i < 64; i++) { mod[2 * i] = norm * pts[i][0]; mod[2 * i + 1] = norm * pts[i][1]; }
+}
+float nbo_sigma_apsk64(float EbN) { return (float)sqrt(1.0 / (2.0 * pow(10, EbN / 10.0))); }      /* :232 */
+/* channel.c:234-263: noisy[N][2] */
+void nbo_channel_noise_apsk64(const nbo_code *c, nbo_rng *r, const int *nbin, float EbN, float *noisy)
+{
+    const double PI = 3.1415926536;
+    const float sigma = nbo_sigma_apsk64(EbN);
+    float mod[128];
+    int n, q;
+    nbo_apsk64_table(mod);
+    for (n = 0; n < c->N; n++) {
+        int som = 0;
+        for (q = 0; q < 6; q++) som = som + nbin[n * 6 + q] * (1 << q);
+        for (q = 0; q < 2; q++) {
+            float u = my_drand48(r);
+            float v = my_drand48(r);
+            noisy[2 * n + q] = (float)(mod[2 * som + q] + sigma * sqrt(-2.0 * log(u)) * cos(2.0 * PI * v));
+        }
+    }
+}
+/* channel.c:266-291: TMP[k] = (I - mI)^2 / (2 sigma^2) + (Q - mQ)^2 / (2 sigma^2), f32 squares, f64 divisions and sum */
+void nbo_channel_llr_apsk64(const nbo_code *c, const float *noisy, float sigma, float *llr)
+{
+    float mod[128];
+    int n, k, q;
+    nbo_apsk64_table(mod);
+    for (n = 0; n < c->N; n++)
+        for (k = 0; k < 64; k++) {
+            int som = 0;
+            float d0, d1;
+            for (q = 0; q < 6; q++) som = som + c->bingf[k * 6 + q] * (1 << q);
+            d0 = noisy[2 * n] - mod[2 * som]; d1 = noisy[2 * n + 1] - mod[2 * som + 1];
+            llr[(size_t)n * 64 + k] = (float)((double)(d0 * d0) / (2.0 * (double)(float)(sigma * sigma)) +
+                                              (double)(d1 * d1) / (2.0 * (double)(float)(sigma * sigma)));
+        }
+}
+
 /* channel.c:78-91: full selection sort of one symbol's LLR vector (strict <, init 1e5 / -1) */
 void nbo_sort_intrinsic(const nbo_code *c, const float *llr, float *illr, int *igf)
 {

@@ -61,6 +61,11 @@ float nbo_sigma(const nbo_code *c, float EbN);                                  
 void nbo_channel_noise(const nbo_code *c, nbo_rng *r, const int *nbin, float EbN, float *noisy); /* channel.c:52-62 */
 void nbo_channel_llr(const nbo_code *c, const float *noisy, float sigma, float *llr);  /* channel.c:66-76 */
 void nbo_sort_intrinsic(const nbo_code *c, const float *llr, float *illr, int *igf);   /* channel.c:78-91 */
+/* 64-APSK channel (ModelChannel_AWGN_64, channel.c:112-312), GF(64) codes */
+void nbo_apsk64_table(float *mod /*[64][2]*/);                                         /* channel.c:133-222 */
+float nbo_sigma_apsk64(float EbN);                                                     /* channel.c:232 */
+void nbo_channel_noise_apsk64(const nbo_code *c, nbo_rng *r, const int *nbin, float EbN, float *noisy /*[N][2]*/);   /* :234-263 */
+void nbo_channel_llr_apsk64(const nbo_code *c, const float *noisy, float sigma, float *llr);                        /* :266-291 */
 
 void nbo_select_nm(const float *row, int GF, int n_m, float *out_llr, int *out_gf);    /* NB_LDPC.c:354-374 */
 void nbo_elementary_step(const float *in1, const float *in2, const int *idx1, const int *idx2,

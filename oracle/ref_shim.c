@@ -112,6 +112,19 @@ void refshim_channel_bpsk(refshim_t *h, const int *nbin, float EbN, float *illr,
     free(NBIN);
 }
 
+/* ModelChannel_AWGN_64 (channel.c:112): outputs sorted intrinsic LLR/GF [N*GF]; draws from the process-wide drand48 state */
+void refshim_channel_apsk64(refshim_t *h, const int *nbin, float EbN, float *illr, int *igf)
+{
+    int N = h->code.N, lg = h->code.logGF, GF = h->code.GF, n, q, idum = -1;
+    int **NBIN = calloc(N, sizeof(int *));
+    for (n = 0; n < N; n++) { NBIN[n] = calloc(lg, sizeof(int)); for (q = 0; q < lg; q++) NBIN[n][q] = nbin[n * lg + q]; }
+    ModelChannel_AWGN_64(&h->code, &h->decoder, NBIN, EbN, &idum);
+    memcpy(illr, h->decoder.intrinsic_LLR[0], sizeof(float) * N * GF);
+    memcpy(igf, h->decoder.intrinsic_GF[0], sizeof(int) * N * GF);
+    for (n = 0; n < N; n++) free(NBIN[n]);
+    free(NBIN);
+}
+
 /* ElementaryStep (bubble_decoder.c:316) */
 void refshim_elementary_step(refshim_t *h, const float *in1, const float *in2, const int *idx1, const int *idx2,
                              float *out, int *idxout, int nbMax, int nbOper)

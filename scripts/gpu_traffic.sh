@@ -21,7 +21,7 @@ rd, wr = val('dram__bytes_read.sum'), val('dram__bytes_write.sum')
 out = {"workload": "$WL", "ecn": "$ECN", "frames": pre["roofline"]["frames_per_launch"], "dram_bytes_read": rd, "dram_bytes_write": wr,
        "dram_bytes_per_launch": rd + wr, "kernel_ms": pre["roofline"]["kernel_ms"], "kernel_ms_under_ncu": val('gpu__time_duration.sum'),
        "warp_instructions": val('smsp__inst_executed.sum'), "algorithmic_bytes_per_launch": pre["roofline"]["bytes_per_frame"] * pre["roofline"]["frames_per_launch"],
-       "git": pre.get("git"), "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one launch of the bench's resident-input step"}
+       "git": pre.get("git"), "source_id": pre.get("source_id"), "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one launch of the bench's resident-input step"}
 out["traffic_over_algorithmic"] = out["dram_bytes_per_launch"] / out["algorithmic_bytes_per_launch"]
 json.dump(out, open('gpurun_out/traffic_${WL}_$ECN.json', 'w'), indent=1)
 print('TRAFFIC', json.dumps(out))

@@ -44,7 +44,7 @@ CASES = [
     ("n96_gf64_nm20_synd", 12, 10, "matrices/N96_K48_GF64", 2.0, 20, 0.3, 25, 3, True, 1, "ubs", (19, 15, 5, 1000, 25)),
     ("mat24_n480_nm20_synd", 4, 10, "matrices/Mat24_N480_M240", 1.5, 20, 0.3, 25, 2, False, 0, "ubs", (19, 15, 5, 1000, 25)),
     ("mat24_n480_nm16_synd_small", 3, 10, "matrices/Mat24_N480_M240", 1.5, 16, 0.3, 25, 2, False, 0, "ubs", (15, 6, 3, 150, 12)),
-    ("ad_r12_gf256_nm20_synd", 1, 10, "matrices/AD_64800_R12_GF256", 2.0, 20, 0.3, 25, 2, False, 0, "ubs", (19, 15, 5, 1000, 25)),
+    ("ad_r12_gf256_nm20_synd", 3, 10, "matrices/AD_64800_R12_GF256", 2.0, 20, 0.3, 25, 2, False, 0, "ubs", (19, 15, 5, 1000, 25)),
 ]
 
 
@@ -117,6 +117,25 @@ def make(case):
                                                            os.path.getsize(path) / 1024))
 
 
+def make_apsk64():
+    """tests/golden/channels/apsk64_n96_gf64.npz: the reference's ModelChannel_AWGN_64 (channel.c:112-312) through
+    oracle/_ref/libref.so on the unseeded drand48 stream: per frame the codeword bits and the sorted intrinsic LLR / GF."""
+    from common import matrix_path
+    r = ol.RefShim(matrix_path("matrices/N96_K48_GF64"), n_m=20, encoder=True)
+    r.seed_default()
+    ebn = 9.0
+    nbin, illr, igf = [], [], []
+    for _ in range(6):
+        _, nb = r.random_codeword()
+        il, ig = r.channel_apsk64(nb, ebn)
+        nbin.append(nb); illr.append(il); igf.append(ig)
+    os.makedirs(os.path.join(HERE, "channels"), exist_ok=True)
+    path = os.path.join(HERE, "channels", "apsk64_n96_gf64.npz")
+    np.savez_compressed(path, matrix="matrices/N96_K48_GF64", ebn=np.float32(ebn), nbin=np.stack(nbin).astype(np.int8),
+                        illr=np.stack(illr), igf=np.stack(igf).astype(np.int16))
+    print("channels/apsk64_n96_gf64   frames=6  %.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     if not ol.have_ref():
         ol.build_oracle()
@@ -124,3 +143,5 @@ if __name__ == "__main__":
     for c in CASES:
         if not sel or c[0] in sel:
             make(c)
+    if not sel or "apsk64" in sel:
+        make_apsk64()

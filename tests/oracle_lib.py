@@ -77,6 +77,11 @@ class Oracle:
             L.nbo_rng_skip.argtypes = [C.POINTER(NboRng), C.c_uint64]
             L.nbo_channel_noise.argtypes = [C.POINTER(NboCode), C.POINTER(NboRng), c_int_p, C.c_float, c_float_p]
             L.nbo_channel_llr.argtypes = [C.POINTER(NboCode), c_float_p, C.c_float, c_float_p]
+            L.nbo_apsk64_table.argtypes = [c_float_p]
+            L.nbo_sigma_apsk64.restype = C.c_float
+            L.nbo_sigma_apsk64.argtypes = [C.c_float]
+            L.nbo_channel_noise_apsk64.argtypes = [C.POINTER(NboCode), C.POINTER(NboRng), c_int_p, C.c_float, c_float_p]
+            L.nbo_channel_llr_apsk64.argtypes = [C.POINTER(NboCode), c_float_p, C.c_float, c_float_p]
             L.nbo_check_node_bubble.argtypes = [C.POINTER(NboCode), C.c_int, c_float_p, c_int_p, c_float_p, c_int_p,
                                                 C.c_int, C.c_int, C.c_float]
             L.nbo_check_node_syndrome.argtypes = [C.POINTER(NboCode), C.c_int, c_float_p, c_int_p, c_float_p, c_int_p,
@@ -146,6 +151,27 @@ class Oracle:
         noisy = np.ascontiguousarray(noisy, np.float32)
         llr = np.zeros((self.N, self.GF), np.float32)
         self.lib().nbo_channel_llr(self.h, _fp(noisy), C.c_float(sigma), _fp(llr))
+        return llr
+
+    # ---- 64-APSK channel (ModelChannel_AWGN_64), GF(64) codes ----
+    def apsk64_table(self):
+        mod = np.zeros((64, 2), np.float32)
+        self.lib().nbo_apsk64_table(_fp(mod))
+        return mod
+
+    def sigma_apsk64(self, ebn):
+        return self.lib().nbo_sigma_apsk64(C.c_float(ebn))
+
+    def channel_noise_apsk64(self, nbin, ebn):
+        nbin = np.ascontiguousarray(nbin, np.int32)
+        noisy = np.zeros((self.N, 2), np.float32)
+        self.lib().nbo_channel_noise_apsk64(self.h, C.byref(self.rng), _ip(nbin), C.c_float(ebn), _fp(noisy))
+        return noisy
+
+    def channel_llr_apsk64(self, noisy, sigma):
+        noisy = np.ascontiguousarray(noisy, np.float32)
+        llr = np.zeros((self.N, self.GF), np.float32)
+        self.lib().nbo_channel_llr_apsk64(self.h, _fp(noisy), C.c_float(sigma), _fp(llr))
         return llr
 
     def sort_intrinsic(self, llr):
@@ -257,7 +283,7 @@ class RefShim:
             L.refshim_rate.restype = C.c_float
             L.refshim_rate.argtypes = [C.c_void_p]
             for n in ("refshim_info", "refshim_graph", "refshim_tables", "refshim_random_codeword",
-                      "refshim_channel_bpsk", "refshim_elementary_step", "refshim_check_node",
+                      "refshim_channel_bpsk", "refshim_channel_apsk64", "refshim_elementary_step", "refshim_check_node",
                       "refshim_decision_syndrome", "refshim_build_config", "refshim_get_config",
                       "refshim_syndrome_ems"):
                 getattr(L, n).argtypes = None
@@ -294,6 +320,13 @@ class RefShim:
         nbin = np.ascontiguousarray(nbin, np.int32)
         il = np.zeros((self.N, self.GF), np.float32); ig = np.zeros((self.N, self.GF), np.int32)
         self.lib().refshim_channel_bpsk(self.h, _ip(nbin), C.c_float(ebn), _fp(il), _ip(ig))
+        return il, ig
+
+    def channel_apsk64(self, nbin, ebn):
+        """ModelChannel_AWGN_64 of the reference on the process-wide drand48 state: sorted intrinsic LLR / GF"""
+        nbin = np.ascontiguousarray(nbin, np.int32)
+        il = np.zeros((self.N, self.GF), np.float32); ig = np.zeros((self.N, self.GF), np.int32)
+        self.lib().refshim_channel_apsk64(self.h, _ip(nbin), C.c_float(ebn), _fp(il), _ip(ig))
         return il, ig
 
     def elementary_step(self, in1, in2, idx1, idx2, n_m, nb_oper):

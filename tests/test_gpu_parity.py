@@ -524,6 +524,60 @@ def test_config4_multi_wave_against_oracle_short_lists():
 
 
 # ---------------------------------------------------------------------------------------------------
+# 64-APSK channel (ModelChannel_AWGN_64, channel.c:112-312): SURVEY 8f row 2
+# ---------------------------------------------------------------------------------------------------
+def test_apsk64_intake_kernel_equals_oracle_and_reference_vectors():
+    """LLR part of ModelChannel_AWGN_64 on the GPU: dense LLR bit-equal to the oracle, the sorted intrinsic_LLR / intrinsic_GF
+    bit-equal to the vectors recorded from the reference (tests/golden/channels/apsk64_n96_gf64.npz)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "channels", "apsk64_n96_gf64.npz"))
+    path = matrix_path(str(z["matrix"]))
+    code = nbldpc.Code(path)
+    o = ol.Oracle(path, code.dialect)
+    code.prepare_encoder(); code.rng_default()
+    ebn = float(z["ebn"]); sigma = nbldpc.sigma_apsk64(ebn)
+    noisy = []
+    for f in range(z["nbin"].shape[0]):
+        _, nb = code.random_codeword()
+        assert (nb == z["nbin"][f]).all()
+        noisy.append(code.noise_apsk64(nb, ebn))
+    noisy = np.stack(noisy)
+    d = nbldpc.Decoder(code, 20, 25, 10, 0.3, max_batch=len(noisy))
+    llr, il, ig = d.channel_apsk64(noisy, sigma, want_sorted=True)
+    for f in range(len(noisy)):
+        assert llr[f].tobytes() == o.channel_llr_apsk64(noisy[f], sigma).tobytes(), f
+        assert il[f].tobytes() == z["illr"][f].tobytes() and (ig[f] == z["igf"][f]).all(), f
+    o.close(); d.close()
+
+
+@pytest.mark.parametrize("rel,ebn", [("matrices/N96_K48_GF64", 8.0), ("matrices/Mat24_N480_M240", 10.3)])
+def test_apsk64_decode_equals_oracle(rel, ebn):
+    """nbgpu_decode_apsk64 (intake fused into the decoder) against the oracle's 64-APSK LLR + decode loop, frames that converge
+    and frames that do not."""
+    path = matrix_path(rel)
+    code = nbldpc.Code(path)
+    o = ol.Oracle(path, code.dialect)
+    code.prepare_encoder(); code.rng_default()
+    sigma = nbldpc.sigma_apsk64(ebn)
+    B = 48
+    noisy = np.stack([code.noise_apsk64(code.random_codeword()[1], ebn) for _ in range(B)])
+    d = nbldpc.Decoder(code, 16, 25, 10, 0.3, max_batch=B)
+    dec, synd, it = d.decode_apsk64(noisy, sigma)
+    assert len(set(it.tolist())) > 1, "pick an Eb/N0 at which the frames differ in iterations"
+    for f in range(B):
+        r = o.decode_frame(o.channel_llr_apsk64(noisy[f], sigma), 16, 25, 10, 0.3)
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"] and it[f] == r["iters"], f
+    o.close(); d.close()
+
+
+def test_apsk64_needs_gf64():
+    code = nbldpc.Code(matrix_path("matrices/KN/N96_K48_GF256.txt"))
+    d = nbldpc.Decoder(code, 20, 25, 10, 0.3, max_batch=2)
+    with pytest.raises(nbldpc.NbgpuError):
+        d.decode_apsk64(np.zeros((2, code.N, 2), np.float32), 0.3)
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------------
 # Monte-Carlo statistics: the C driver (csrc/nbldpc_mc.c) and the sharded loop (multigpu.py) against the stock binary
 # ---------------------------------------------------------------------------------------------------
 KNOWN = [  # args of the reference binary, console (undetected, err frames, frames, bit errors, avr_it), frames in the results file

@@ -273,3 +273,24 @@ def test_c_driver_is_built_and_fails_loudly_without_a_gpu(tmp_path):
         r = subprocess.run([exe, "4", "10", matrix_path("matrices/N96_K48_GF64"), "3.0", "20", "0.3", "25"], cwd=tmp_path,
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stdout
+
+
+def test_apsk64_host_side_equals_oracle():
+    """Host side of the 64-APSK channel (nbgpu_apsk64_table, nbgpu_sigma_apsk64, nbgpu_awgn_apsk64_noise): constellation, sigma
+    and the noisy samples on the reference's drand48 stream equal the oracle's, bit for bit; other fields are refused."""
+    path = matrix_path("matrices/N96_K48_GF64")
+    code = nbldpc.Code(path)
+    o = ol.Oracle(path)
+    assert nbldpc.apsk64_table().tobytes() == o.apsk64_table().tobytes()
+    code.prepare_encoder(); code.rng_default(); o.prepare_encoder(); o.rng_default()
+    for ebn in (4.0, 9.0):
+        assert nbldpc.sigma_apsk64(ebn) == o.sigma_apsk64(ebn)
+        for _ in range(5):
+            _, nb = code.random_codeword()
+            _, nb_o = o.random_codeword()
+            assert (nb == nb_o).all()
+            assert code.noise_apsk64(nb, ebn).tobytes() == o.channel_noise_apsk64(nb_o, ebn).tobytes()
+    o.close()
+    c256 = nbldpc.Code(matrix_path("matrices/KN/N96_K48_GF256.txt"))
+    with pytest.raises(nbldpc.NbgpuError):
+        c256.noise_apsk64(None, 9.0)

@@ -2,6 +2,8 @@
  * against the golden fixtures generated from the unmodified reference (always), and
  * against the reference objects themselves (oracle/_ref/libref.so) when they are present.
 The reference ships no tests or golden vectors of its own."""
+import os
+
 import numpy as np
 import pytest
 
@@ -212,6 +214,41 @@ def test_frame_source_and_channel_equal_reference():
         d_r, s_r = r.decision_syndrome(llr)
         assert (d_r == o.decision(llr)).all() and s_r == o.syndrome(d_r)
         assert o.syndrome(cw_o) == 0
+    o.close()
+
+
+def test_apsk64_channel_port_equals_committed_reference_vectors():
+    """64-APSK channel (ModelChannel_AWGN_64, channel.c:112-312): the oracle port on the unseeded drand48
+    stream against tests/golden/channels/apsk64_n96_gf64.npz (sorted intrinsic LLR / GF recorded from the reference)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "channels", "apsk64_n96_gf64.npz"))
+    o = ol.Oracle(matrix_path(str(z["matrix"])))
+    o.prepare_encoder(); o.rng_default()
+    ebn = float(z["ebn"])
+    for f in range(z["nbin"].shape[0]):
+        _, nb = o.random_codeword()
+        assert (nb == z["nbin"][f]).all()
+        noisy = o.channel_noise_apsk64(nb, ebn)
+        il, ig = o.sort_intrinsic(o.channel_llr_apsk64(noisy, o.sigma_apsk64(ebn)))
+        assert il.tobytes() == z["illr"][f].tobytes() and (ig == z["igf"][f]).all(), f
+    mod = o.apsk64_table()
+    assert abs(float((mod.astype(np.float64) ** 2).sum()) / 64 - 1.0) < 1e-6          # average power 1, channel.c:205-211
+    o.close()
+
+
+@needs_ref
+def test_apsk64_channel_port_equals_reference():
+    p = matrix_path("matrices/N96_K48_GF64")
+    r = ol.RefShim(p, n_m=20, encoder=True)
+    o = ol.Oracle(p)
+    o.prepare_encoder(); o.rng_default(); r.seed_default()
+    for ebn in (5.0, 9.0, 14.0):
+        for _ in range(8):
+            _, nb_r = r.random_codeword()
+            il_r, ig_r = r.channel_apsk64(nb_r, ebn)
+            _, nb_o = o.random_codeword()
+            noisy = o.channel_noise_apsk64(nb_o, ebn)
+            il_o, ig_o = o.sort_intrinsic(o.channel_llr_apsk64(noisy, o.sigma_apsk64(ebn)))
+            assert (nb_r == nb_o).all() and il_r.tobytes() == il_o.tobytes() and (ig_r == ig_o).all()
     o.close()
 
 
