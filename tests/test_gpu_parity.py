@@ -660,6 +660,33 @@ def test_c_driver_stops_at_the_40th_erroneous_frame_in_frame_order(tmp_path):
     assert outs[0] == outs[1] == outs[2], outs
 
 
+def test_c_driver_ebn_sweep_reuses_one_context(tmp_path):
+    """BASELINE config 2 is an Eb/N0 sweep (start.sh:14-23: one process per point).  `nbldpc_mc ... first:last:step` runs the
+    points one after the other on ONE context; every point must print and log what its own process would."""
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(nbldpc.LIB_PATH), "nbldpc_mc")
+    pat = r"<(\d+)> FER=\s*(\d+)\s*/\s*(\d+)\s*=\s*[\d.]+\s*BER=\s*(\d+)\s*/\s*x\s*=\s*[\d.eE+-]+\s*avr_it=([\d.]+)"
+    mat = matrix_path("matrices/Mat24_N480_M240")
+
+    def run(ebn, sub):
+        d = tmp_path / sub
+        os.makedirs(d / "data")
+        r = subprocess.run([exe, "200", "10", mat, ebn, "16", "0.3", "25", "100", "0"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:]
+        lines = list((d / "data").glob("results_*.txt"))[0].read_text().splitlines()
+        return r.stdout, [ln.split("time:")[0] for ln in lines]
+
+    out, lines = run("1.5:2.0:0.25", "sweep")
+    blocks = out.split("---- Eb/No = ")[1:]
+    assert len(blocks) == 3 and len(lines) == 3
+    last = [re.findall(pat, b)[-1] for b in blocks]
+    assert (int(last[0][1]), int(last[0][2]), int(last[0][3]), last[0][4]) == (11, 200, 165, "6.23")      # SURVEY 8c known answer at 1.5 dB
+    for i, ebn in enumerate(["1.5", "1.75", "2.0"]):
+        o1, l1 = run(ebn, "single%d" % i)
+        assert re.findall(pat, o1)[-1] == last[i] and l1 == [lines[i]], (ebn, l1, lines[i])
+
+
 def test_reference_main_with_gpu_check_node(tmp_path):
     """The compiled drop-in (boundary 1, include/bubble_decoder.h:17): oracle/_ref/essai_gpucn is the reference's unmodified
     main() built with -DCheckPassLogEMS=nbgpu_CheckPassLogEMS and linked against libnbldpc_b200.so through the maintainer-side
