@@ -144,6 +144,7 @@ template <int Q> struct WarpMem {
     uint32_t *scr[NE];       /* phase 1, per in-flight edge: selection queue (sorted keys)                          */
     uint32_t *sel[NE];       /* phase 1: winners of the selection rounds (NB_SEL_CAPTURE = 0 / GF(16) half-warp)   */
     float *row3[NE];         /* phase 3, per in-flight edge: clean row                                              */
+    uint32_t rowa[NE], scra[NE], sela[NE], row3a[NE];      /* the same four as shared-window addresses (hot loops)   */
     uint32_t mask;           /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided (shared address)  */
     TileMeta meta;           /* [cpw] {first edge | degree << 24 (0 = skip), frame}                         */
     uint32_t *ew;            /* [cpw][dc_max] einfo words of the tile's edges (one coalesced load per tile) */
@@ -159,6 +160,7 @@ template <int Q> struct WarpMem {
             scr[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + rows + e * QTraits<Q>::SCR_WORDS;
             sel[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + rows + NE * QTraits<Q>::SCR_WORDS + e * 36;
             row3[e] = reinterpret_cast<float *>(wb + a.wb_scr3) + e * Q;
+            rowa[e] = smem_u32(row[e]); scra[e] = smem_u32(scr[e]); sela[e] = smem_u32(sel[e]); row3a[e] = smem_u32(row3[e]);
         }
         mask = smem_u32(wa + a.wa_mask);
         meta.p = reinterpret_cast<int4 *>(wa + a.wa_meta);
@@ -506,7 +508,7 @@ __device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm
     const Lists &ls = wm.ls;
     const int dcm = a.dc_max, n_m = a.n_m, rs = a.rec_stride;
 #pragma unroll
-    for (int e = 0; e < NE; e++) fill_row<Q>(wm.row[e], lane, NB_ROW_CLEAN);
+    for (int e = 0; e < NE; e++) fill_row_s<Q>(wm.rowa[e], lane, NB_ROW_CLEAN);
     __syncwarp();
     for (int c = 0; c < cnt; c++) {
         const int4 mt = wm.meta[c];
@@ -532,16 +534,13 @@ __device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm
 #pragma unroll
             for (int e = 0; e < NE; e++) {
                 float cv[VPL];
-                expand_record<Q>(r[e], lane, wm.row[e], cv, minform);
+                expand_record<Q>(r[e], lane, wm.rowa[e], cv, minform);
 #pragma unroll
                 for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
                 if (NB_PARK_MVC && t + e < dc) store_row_hint<Q>(prow[e], lane, v[e], pol_keep);     /* parked for phase 3 (NB_LDPC.c:448 adds this vector) */
             }
             float llr[NE]; int sym[NE];
-            uint32_t *scr[NE], *sel[NE];
-#pragma unroll
-            for (int e = 0; e < NE; e++) { scr[e] = wm.scr[e]; sel[e] = wm.sel[e]; }
-            select_edges<Q, NE>(v, lane, scr, sel, n_m, llr, sym, a.slow_counter);
+            select_edges<Q, NE>(v, lane, wm.scra, wm.sela, n_m, llr, sym, a.slow_counter);
 #pragma unroll
             for (int e = 0; e < NE; e++) {
                 if (t + e < dc) {
@@ -567,7 +566,7 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
     const Lists &ls = wm.ls;
     const int dcm = a.dc_max, n_m = a.n_m;
 #pragma unroll
-    for (int e = 0; e < NE; e++) fill_row<Q>(wm.row3[e], lane, NB_ROW_CLEAN);
+    for (int e = 0; e < NE; e++) fill_row_s<Q>(wm.row3a[e], lane, NB_ROW_CLEAN);
     __syncwarp();
     for (int c = 0; c < cnt; c++) {
         const int4 mt = wm.meta[c];
@@ -593,7 +592,7 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
                     const uint32_t var = ei[e] & 0xfffffu;
                     if (!NB_PARK_MVC) {
                         float cv[VPL];
-                        expand_record<Q>(old[e], lane, wm.row3[e], cv, minform);
+                        expand_record<Q>(old[e], lane, wm.row3a[e], cv, minform);
 #pragma unroll
                         for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334, same operands as phase 1 */
                     }
@@ -602,7 +601,7 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
                     const RecView nr = finish_list<Q, CLOSED>(ls, li, (ei[e] >> 20) & 0xff, gf, a.offset, lane);
                     store_record(rec0, (uint32_t)te, rl, nr, n_m, lane);
                     float mcv[VPL];
-                    expand_record<Q>(nr, lane, wm.row3[e], mcv, minform);    /* :262-281 */
+                    expand_record<Q>(nr, lane, wm.row3a[e], mcv, minform);    /* :262-281 */
 #pragma unroll
                     for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
                     store_row_hint<Q>(reinterpret_cast<float *>(app_f + var * (uint32_t)(Q * 4)), lane, v[e], pol_first);
@@ -764,10 +763,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);
                             }
                             float llr[NE]; int sym[NE];
-                            uint32_t *scr[NE], *sel[NE];
-#pragma unroll
-                            for (int e = 0; e < NE; e++) { scr[e] = wm.scr[e]; sel[e] = wm.sel[e]; }
-                            select_edges<Q, NE>(v, lane, scr, sel, n_m, llr, sym, a.slow_counter);
+                            select_edges<Q, NE>(v, lane, wm.scra, wm.sela, n_m, llr, sym, a.slow_counter);
 #pragma unroll
                             for (int e = 0; e < NE; e++) {
                                 if (t + e < dc && lane < n_m) {
@@ -846,8 +842,8 @@ __global__ void __launch_bounds__(UNIT_NT) select_kernel(const float *rows, floa
     __shared__ uint32_t scr_s[UW][QTraits<Q>::SCR_WORDS + 64];     /* + slack: a lane that popped the +inf row reads one row further */
     __shared__ uint32_t sel_s[UW][36];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *scr[1] = { scr_s[warp] };
-    uint32_t *sel[1] = { sel_s[warp] };
+    const uint32_t scr[1] = { smem_u32(scr_s[warp]) };
+    const uint32_t sel[1] = { smem_u32(sel_s[warp]) };
     for (int r = blockIdx.x * UW + warp; r < B; r += gridDim.x * UW) {
         float v[1][VPL];
         load_row<Q>(rows + (size_t)r * Q, lane, v[0]);
@@ -910,13 +906,13 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
         if (lane < cnt) wm.meta.set(lane, e0, dc, 0u, 0u, 0u);
         __syncwarp();
         tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
-        fill_row<Q>(wm.row3[0], lane, NB_ROW_CLEAN);       /* aliases the input lists, dead after the elementary steps (degree 2: a region of its own) */
+        fill_row_s<Q>(wm.row3a[0], lane, NB_ROW_CLEAN);       /* aliases the input lists, dead after the elementary steps (degree 2: a region of its own) */
         __syncwarp();
         for (int c = 0; c < cnt; c++)
             for (int t = 0; t < dc; t++) {
                 const RecView nr = finish_list<Q, CLOSED>(ls, ls.idx(c, id_out(dc, t), dc), a.hval[e0 + t], gf, a.offset, lane);
                 float mcv[VPL];
-                expand_record<Q>(nr, lane, wm.row3[0], mcv, a.offset >= 0.0f);
+                expand_record<Q>(nr, lane, wm.row3a[0], mcv, a.offset >= 0.0f);
                 float *dst = cllr + ((size_t)(b0 + c) * dc + t) * Q;
                 store_row<Q>(dst, lane, mcv);
                 int *gdst = cgf + ((size_t)(b0 + c) * dc + t) * Q;

@@ -159,6 +159,31 @@ template <int Q> __device__ __forceinline__ void fill_row(float *row, int lane, 
     }
 }
 
+/* the same row moves on a shared-window address (no generic-pointer arithmetic in the hot loops) */
+template <int Q> __device__ __forceinline__ void lds_row(uint32_t row, int lane, float (&v)[QTraits<Q>::VPL])
+{
+    if constexpr (Q == 256) {
+        const uint32_t a = row + lane * 16;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+512];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
+    } else if constexpr (Q == 64) {
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(row + lane * 8));
+    } else {
+        v[0] = (lane < Q) ? lds_f32(row + 4 * lane) : NB_SENT;
+    }
+}
+template <int Q> __device__ __forceinline__ void fill_row_s(uint32_t row, int lane, float x)
+{
+    if constexpr (Q == 256) {
+        const uint32_t a = row + lane * 16;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+512], {%1, %1, %1, %1};" :: "r"(a), "f"(x) : "memory");
+    } else if constexpr (Q == 64) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %1};" :: "r"(row + lane * 8), "f"(x) : "memory");
+    } else {
+        if (lane < Q) sts_f32(row + 4 * lane, x);
+    }
+}
+
 /* ---- stored C->V message of one edge ("record"): llr[n_m] f32 | pad to 8 | sat f32 | stp i32 | sym[n_m] u8 ----
  * A dense CtoV row is "stp explicit (symbol, LLR) pairs + the constant sat everywhere else"
  * (bubble_decoder.c:262-270), so the record is lossless. */
@@ -199,16 +224,17 @@ __device__ __forceinline__ void store_record(uint8_t *ctov_f, uint32_t ed, const
  * bubble_decoder.c:264), so the merge is one FMNMX per value; otherwise a compare + select. */
 #define NB_ROW_CLEAN __int_as_float(0x7f800000)
 template <int Q>
-__device__ __forceinline__ void expand_record(const RecView &r, int lane, float *scr, float (&c)[QTraits<Q>::VPL], bool minform)
+__device__ __forceinline__ void expand_record(const RecView &r, int lane, uint32_t scr, float (&c)[QTraits<Q>::VPL], bool minform)
 {
     constexpr int VPL = QTraits<Q>::VPL;
     const bool mine = lane < r.stp;
-    if (mine) scr[r.sym] = r.llr;
+    const uint32_t slot = scr + 4 * (uint32_t)r.sym;
+    if (mine) sts_f32(slot, r.llr);
     __syncwarp();
     float x[VPL];
-    load_row<Q>(scr, lane, x);
+    lds_row<Q>(scr, lane, x);
     __syncwarp();
-    if (mine) scr[r.sym] = NB_ROW_CLEAN;
+    if (mine) sts_f32(slot, NB_ROW_CLEAN);
     if (minform) {
 #pragma unroll
         for (int j = 0; j < VPL; j++) c[j] = fminf(x[j], r.sat);
@@ -300,7 +326,7 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
  * place with full comparisons; otherwise that edge re-runs the exact scan (same semantics as the
  * reference loop).
  *
- * scr[e]: SCR_WORDS u32 of warp-private scratch (free on entry, free on return); sel[e]: 36 u32.
+ * scr[e]: SCR_WORDS u32 of warp-private scratch (free on entry, free on return); sel[e]: 36 u32; both as shared-window addresses.
  * Result: lane k < n_m holds (out_llr[e], out_sym[e]) = k-th entry of edge e.
  */
 #ifndef NB_SEL_CAPTURE
@@ -314,8 +340,8 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
 #define NB_SEL_LOOKAHEAD 0
 #endif
 template <int Q, int NEDG>
-__device__ __forceinline__ void select_edges(const float (&mvc)[NEDG][QTraits<Q>::VPL], int lane, uint32_t *(&scr)[NEDG],
-                                             uint32_t *(&sel)[NEDG], int n_m, float (&out_llr)[NEDG], int (&out_sym)[NEDG],
+__device__ __forceinline__ void select_edges(const float (&mvc)[NEDG][QTraits<Q>::VPL], int lane, const uint32_t (&scr)[NEDG],
+                                             const uint32_t (&sel)[NEDG], int n_m, float (&out_llr)[NEDG], int (&out_sym)[NEDG],
                                              unsigned *slow_counter)
 {
     constexpr int VPL = QTraits<Q>::VPL;
@@ -349,18 +375,19 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NEDG][QTraits<Q>
         }
         sort_keys<VPL>(key);
         bad[e] = active && key[VPL - 1] >= 0x7f800000u;
+        const uint32_t col = scr[e] + 4 * lane;            /* the lane's column of the queue [rank][lane] */
 #pragma unroll
-        for (int j = 0; j < VPL; j++) scr[e][j * 32 + lane] = key[j];
-        scr[e][VPL * 32 + lane] = NB_KEY_INF;
+        for (int j = 0; j < VPL; j++) sts_u32(col + 128 * j, key[j]);
+        sts_u32(col + 128 * VPL, NB_KEY_INF);
         head[e] = key[0];
 #if NB_SEL_LOOKAHEAD
         nk[e] = VPL > 1 ? key[VPL > 1 ? 1 : 0] : NB_KEY_INF;     /* the lane's next key is already in a register ... */
-        nxt[e] = smem_u32(scr[e] + 32 + lane);          /* ... and this is its row */
+        nxt[e] = col + 128;                              /* ... and this is its row */
 #else
         nk[e] = 0;
-        nxt[e] = smem_u32(scr[e] + lane);              /* row of the lane's current head */
+        nxt[e] = col;                                   /* row of the lane's current head */
 #endif
-        selp[e] = smem_u32(sel[e]);
+        selp[e] = sel[e];
         mine[e] = NB_KEY_INF;
     }
     if constexpr (Q == 16 && NEDG == 2) {
@@ -491,7 +518,7 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NEDG][QTraits<Q>
     for (int e = 0; e < NEDG; e++) NB_SEL_PEEK(e);
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < NEDG; e++) mine[e] = sel[e][min(lane, rounds - 1)];
+    for (int e = 0; e < NEDG; e++) mine[e] = lds_u32(sel[e] + 4 * min(lane, rounds - 1));
 #endif
     }
     __syncwarp();

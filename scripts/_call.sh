@@ -1,9 +1,7 @@
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L | head -4
-timeout 900 python -m pytest tests -m gpu -x -q -k "several_devices or apsk64 or reference_main or 40th" 2>&1 | tail -6
-timeout 600 python bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu --no-also --frames 592 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; tail -3 gpurun_out/bench_2gpu.err
-python - <<PY
-import json
-j = json.loads(open('gpurun_out/bench_2gpu.json').read().strip().splitlines()[-1])
-print('2GPU value', round(j['value'], 2), 'e2e', round(j['e2e']['value'], 2), 'n_gpus', j['n_gpus'], 'sharding_check', j.get('sharding_check'))
-PY
+timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+export NO_NCU=1
+bash scripts/gpu_variants.sh AD_64800_R12_GF256 592 "default"
+bash scripts/gpu_variants.sh MatDeclercq_R12_GF64 4096 "default"
+bash scripts/gpu_variants.sh Ahmed_64800_R34_GF16 4096 "default"
+bash scripts/gpu_variants.sh Mat24_N480_M240 65536 "default"
