@@ -448,6 +448,39 @@ def test_full_size_round_trip_and_invariances(rel, n_m, ebn_hi):
     d.close()
 
 
+@pytest.mark.parametrize("rel,n_m,ebn,ecn", [("matrices/N96_K48_GF64", 20, 2.5, 0), ("matrices/Mat24_N480_M240", 16, 1.5, 0),
+                                              ("matrices/KN/N96_K48_GF256.txt", 20, 2.5, 0), ("matrices/Mat24_N480_M240", 20, 1.5, 1)])
+def test_fixed_iteration_mode_equals_oracle_with_forced_passes(rel, n_m, ebn, ecn):
+    """The metric's mode (early termination off, NbIterMax-1 passes for every frame): Decision and Syndrom run only after the
+    last pass on the GPU; decisions, syndrome, iteration count and every APP / CtoV bit must equal the oracle run with the
+    break of NB_LDPC.c:470 disabled -- for frames that would have converged early and for frames that never do."""
+    path = matrix_path(rel)
+    code = nbldpc.Code(path)
+    o = ol.Oracle(path, code.dialect)
+    kw, okw = {}, {}
+    if ecn:
+        cfg = o.build_config_table(int(code.row_deg[0]), n_m - 1, 15, 5, 1000)
+        kw = dict(ecn_kind=1, d1=n_m - 1, d2=15, d3=5, cfg_trunc=1000, n_cv=25)
+        okw = dict(ecn=1, cfg=cfg, n_cv=25)
+    B = 24 if code.N > 100 else 64
+    fr, sigma = product_frames(code, B, ebn)
+    noisy = np.stack([f["noisy"] for f in fr])
+    d = nbldpc.Decoder(code, n_m, 25, 10, 0.3, early_stop=False, max_batch=B, **kw)
+    dec, synd, it = d.decode_noisy(noisy, sigma)
+    assert (it == 10).all()
+    nconv = 0
+    for f in range(B):
+        llr = o.channel_llr(fr[f]["noisy"], sigma)
+        r = o.decode_frame(llr, n_m, 25, 10, 0.3, force=True, want_state=(f % 6 == 0), **okw)
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"], f
+        nconv += int(r["synd"] == 0)
+        if f % 6 == 0:
+            app, ctov = d.get_state(f)
+            assert app.tobytes() == r["app"].tobytes() and ctov.tobytes() == r["ctov"].tobytes(), f
+    assert 0 < nconv < B, "the batch should mix frames that converge and frames that do not"
+    o.close(); d.close()
+
+
 def test_full_size_multi_wave_batch_spot_checked_against_oracle():
     """BASELINE config 5 at the operating point of the bench (Eb/N0 2.0 dB, some frames never converge): a batch larger than
     the persistent grid (several frames per CTA, chunked end-to-end path), six frames spot-checked against the oracle"""
