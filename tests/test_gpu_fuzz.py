@@ -33,6 +33,17 @@ CASES = list(range(160))
 
 @pytest.mark.parametrize("seed", CASES)
 def test_random_configuration_equals_oracle(seed, tmp_path):
+    _random_configuration(seed, tmp_path, None)
+
+
+@pytest.mark.parametrize("seed", list(range(0, 48, 3)) + [3, 7, 11, 15])
+def test_random_configuration_with_negative_offset_equals_oracle(seed, tmp_path):
+    """offset < 0 (the command line accepts it): the saturation fill value is below the last list entry, so the record
+    expansion cannot use its min() form (expand_record, minform = false)"""
+    _random_configuration(seed, tmp_path, -0.4 if seed % 2 else -1.5)
+
+
+def _random_configuration(seed, tmp_path, offset_override):
     rng = np.random.default_rng(1000 + seed)
     q = int(rng.choice([16, 64, 256]))
     syndrome = seed % 4 == 3
@@ -53,6 +64,8 @@ def test_random_configuration_equals_oracle(seed, tmp_path):
     n_m = int(rng.integers(5, min(q, 32) + 1))
     nb_oper = int(rng.integers(1, 61))
     offset = float(rng.choice([0.0, 0.3, 1.0, 2.5]))
+    if offset_override is not None:
+        offset = offset_override
     nb_iter_max = int(rng.integers(2, 9))
     early = bool(rng.integers(0, 2))
     frames = int(rng.integers(1, 40))
