@@ -53,20 +53,30 @@ struct SyndMem {
 #define NB_SYND_PERM_BYTES 320
 
 /* bayes(M1 = new LLR, M2 = current LLR), syndrome_decoder.c:2142-2211.  The reference takes double arguments, keeps float
- * locals and multiplies by double constants.  Bit-exact equivalents used here:
+ * locals and multiplies by double constants.  Bit-exact equivalents in f32 (conversions and f64 operations run at a quarter of
+ * the f32 rate or less, and every lane of the walk evaluates this on every hit):
  *   - M1 < M2 on doubles that are floats == the float comparison;
- *   - dif = (float)(M2 - M1): the double difference is kept (one DADD), then rounded;
+ *   - dif = (float)((double)hi - (double)mn) == hi - mn in f32: the double difference is exact while the exponents are less
+ *     than 29 apart (one rounding either way); beyond that mn < 2^-29 hi is below a quarter ulp of hi and both give hi;
  *   - (double)dif < 0.1 / 0.2 / 1 / 2  ==  dif < 0.1f / 0.2f / 1.0f / 2.0f  (0.1f and 0.2f are the first floats above 0.1, 0.2);
  *   - (float)(c * (double)min) for c = 0.5, 0.75, 0.9375: the double product of a float by a 1-4 bit constant is exact, so its
- *     rounding equals the float product; c = 0.825 is not representable and keeps the double multiplication.
- * Branch-free: every lane of the walk evaluates it on every hit, so divergence would cost more than the few extra instructions. */
+ *     rounding equals the float product;
+ *   - c = 0.825 is not representable: with c1 = (float)c, c2 = (float)(c - c1), p = mn*c1, e = fma(mn, c1, -p) (exact),
+ *     t = fma(mn, c2, e), the sum p + t equals (float)(c * (double)mn) for EVERY float mn >= 2^-96 (checked exhaustively over
+ *     all 2^31 non-negative floats, scripts/check_bayes_f32.c; below 2^-96 e or t underflow, 0 is exact again): that range
+ *     keeps the double multiplication behind a branch no real message takes.
+ * Branch-free otherwise: divergence would cost more than the few extra instructions. */
 __device__ __forceinline__ float synd_bayes_sel(float m1, float m2)
 {
     const float mn = fminf(m1, m2), hi = fmaxf(m1, m2);          /* M1 < M2 ? (M1, M2) : (M2, M1); equal values give the same pair */
-    const float dif = __double2float_rn(__dsub_rn((double)hi, (double)mn));
+    const float dif = __fsub_rn(hi, mn);
     const float f = dif < 0.1f ? 0.5f : dif < 0.2f ? 0.75f : dif < 2.0f ? 0.9375f : 1.0f;
     const float a = __fmul_rn(f, mn);
-    const float b = __double2float_rn(__dmul_rn(0.825, (double)mn));
+    const float c1 = 0x1.a66666p-1f, c2 = 0x1.99999ap-27f;       /* 0.825 = c1 + c2 - 2^-52 */
+    const float p = __fmul_rn(mn, c1);
+    const float e = __fmaf_rn(mn, c1, -p);
+    float b = __fadd_rn(p, __fmaf_rn(mn, c2, e));
+    if (((__float_as_uint(mn) & 0x7fffffffu) - 1u) < 0x0f800000u - 1u) b = __double2float_rn(__dmul_rn(0.825, (double)mn));
     return (dif >= 0.2f && dif < 1.0f) ? b : a;
 }
 
@@ -284,30 +294,33 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
         }
     }
     __syncwarp();
-    /* ---- order every symbol group by (LLR, configuration): every lane a run of whole groups of about S/32 entries ---- */
+    /* ---- order every symbol group by (LLR, configuration): every lane a run of whole groups of about S/32 entries, ONE
+     * flat loop over the run's entries (insertion towards the start of the entry's own group) so that the lanes' different
+     * group sizes do not serialise ---- */
     {
         const int gfirst = synd_lane_group(sm, lane);
         int glast = __shfl_down_sync(NB_FULL, gfirst, 1);
         if (lane == 31) glast = 256;
-        int ge = (int)synd_M(sm, (uint32_t)gfirst);
+        const int lo = (int)synd_M(sm, (uint32_t)gfirst), hi_i = (int)synd_M(sm, (uint32_t)glast);
+        uint32_t gcur = (uint32_t)gfirst;
+        int gs = lo, gend = (int)synd_M(sm, gcur + 1u);
 #pragma unroll 1
-        for (int g = gfirst; g < glast; g++) {
-            const int gs = ge;
-            ge = (int)synd_M(sm, (uint32_t)(g + 1));
-            for (int i = gs + 1; i < ge; i++) {
-                const uint32_t k = lds_u32(sm.gkey + 4 * i);
-                unsigned short p;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.gpay + 2 * i));
-                int j = i - 1;
-                while (j >= gs) {
-                    const uint32_t kj = lds_u32(sm.gkey + 4 * j);
-                    unsigned short pj;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pj) : "r"(sm.gpay + 2 * j));
-                    if (!(kj > k || (kj == k && pj > p))) break;
-                    sts_u32(sm.gkey + 4 * (j + 1), kj);
-                    asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * (j + 1)), "h"(pj) : "memory");
-                    j--;
-                }
+        for (int i = lo; i < hi_i; i++) {
+            while (i >= gend) { gcur++; gs = gend; gend = (int)synd_M(sm, gcur + 1u); }
+            const uint32_t k = lds_u32(sm.gkey + 4 * i);
+            unsigned short p;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.gpay + 2 * i));
+            int j = i - 1;
+            while (j >= gs) {
+                const uint32_t kj = lds_u32(sm.gkey + 4 * j);
+                unsigned short pj;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pj) : "r"(sm.gpay + 2 * j));
+                if (!(kj > k || (kj == k && pj > p))) break;
+                sts_u32(sm.gkey + 4 * (j + 1), kj);
+                asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * (j + 1)), "h"(pj) : "memory");
+                j--;
+            }
+            if (j != i - 1) {
                 sts_u32(sm.gkey + 4 * (j + 1), k);
                 asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * (j + 1)), "h"(p) : "memory");
             }
@@ -357,7 +370,9 @@ __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, flo
         const uint32_t mem = (lds_u8(sm.cfgmask + (uint32_t)ps) >> d0) & ndmask;       /* decorrelation, :96-98 */
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if ((mem >> k) & 1u) m[k] = ((have >> k) & 1u) ? synd_bayes_sel(llr, m[k]) : llr;
+            const float nb = synd_bayes_sel(llr, m[k]);
+            const float first = ((have >> k) & 1u) ? nb : llr;
+            m[k] = ((mem >> k) & 1u) ? first : m[k];
         }
         have |= mem;
         if (i + 1 == gend) {                                     /* last syndrome of the symbol: saturation (:198-209) and store */
