@@ -297,9 +297,10 @@ __device__ __forceinline__ SyndMem make_synd_mem(unsigned char *smem, const KArg
     SyndMem sm;
     const uint32_t wb = smem_u32(smem + a.off_wb + warp * a.wb_bytes);
     sm.lists = wb + a.wb_U;
-    sm.gkey = wb + a.sw_key; sm.gpay = wb + a.sw_pay; sm.gfa = wb + a.sw_gf;
-    sm.hist = wb + a.sw_hist; sm.hsat = sm.gkey; sm.cand = wb + a.sw_cand;
-    sm.rows = wb + a.sw_rows; sm.keya = sm.rows;
+    sm.gkey = wb + a.sw_key; sm.hsat = sm.gkey; sm.rows = sm.gkey;          /* region B */
+    sm.keya = wb + a.sw_rows; sm.skey = sm.keya;                            /* region A */
+    sm.gpay = wb + a.sw_pay; sm.gfa = wb + a.sw_gf; sm.hist = wb + a.sw_hist; sm.spay = sm.gfa;
+    sm.cand = wb + a.sw_cand;
     sm.M = wb + a.sw_M; sm.perm = wb + a.sw_perm;
     sm.cfg = smem_u32(smem + a.off_cfg); sm.cfgmask = sm.cfg + (uint32_t)(a.S * a.dc_max);
     sm.lstride = a.lstride; sm.n_m = a.n_m; sm.dc = a.dc_max; sm.S = a.S; sm.n_cv = a.n_cv;
@@ -774,9 +775,9 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                             }
                         }
                         __syncwarp();
-                        synd_prepare(sm, lane);
+                        const bool plain = synd_prepare(sm, lane);
                         for (int d = 0; d < dc; d++) {
-                            if ((d & 3) == 0) synd_walk(sm, d, min(4, dc - d), a.offset, lane);
+                            if ((d & 3) == 0) { if (plain) synd_walk<false>(sm, d, min(4, dc - d), a.offset, lane); else synd_walk<true>(sm, d, min(4, dc - d), a.offset, lane); }
                             const uint32_t out = sm.rows + 1024 * (d & 3);
                             const int t = (int)lds_u32(sm.perm + 4 * d);                   /* un-permute, syndrome_decoder.c:234-253 */
                             const uint32_t ei = wm.ew[c * dcm + t];
@@ -946,9 +947,9 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_synd_kernel(const KArgs a
             sts_u8(list + 4 * n_m + k, (uint32_t)gf_rot_in<Q, CLOSED>(gf, vgf[src] & (Q - 1), a.hval[e0 + t]));
         }
         __syncwarp();
-        synd_prepare(sm, lane);
+        const bool plain = synd_prepare(sm, lane);
         for (int d = 0; d < dc; d++) {
-            if ((d & 3) == 0) synd_walk(sm, d, min(4, dc - d), a.offset, lane);
+            if ((d & 3) == 0) { if (plain) synd_walk<false>(sm, d, min(4, dc - d), a.offset, lane); else synd_walk<true>(sm, d, min(4, dc - d), a.offset, lane); }
             const uint32_t out = sm.rows + 1024 * (d & 3);
             const int t = (int)lds_u32(sm.perm + 4 * d);
             float *dst = cllr + ((size_t)b * dc + t) * Q;
@@ -1163,12 +1164,13 @@ static void plan_smem(KArgs &k, int nw, int cpw)
         int wb2 = 0;
         k.wb_U = wb2; k.wb_R = wb2; wb2 += align_up(k.dc_max * k.lstride, 16);
         k.wb_scr1 = wb2; k.wb_scr3 = wb2;
-        k.sw_key = wb2; wb2 += std::max(std::max(align_up(4 * k.S, 16), align_up(sq, 16)), ((k.dc_max + 1) / 2) * 1024);   /* grouped keys | saturation histograms | selection scratch */
-        k.sw_pay = wb2; wb2 += align_up(2 * k.S, 16);
-        k.sw_gf = wb2; wb2 += align_up(k.S, 16);
+        /* region B: selection scratch | saturation histograms | grouped keys (+16: the rank loop reads up to 3 keys past a group) | 4 output rows */
+        k.sw_key = wb2; wb2 += std::max(std::max(align_up(4 * k.S + 16, 16), align_up(sq, 16)), std::max(4096, ((k.dc_max + 1) / 2) * 1024));
+        k.sw_pay = wb2; wb2 += align_up(2 * k.S, 16);                                    /* payloads of the grouped keys */
+        k.sw_gf = wb2; wb2 += align_up(k.S, 16);                                         /* symbols by configuration; with the next 1024 bytes: sorted payloads (2 S <= S + 1024) */
         k.sw_hist = wb2; wb2 += 1024;                                                    /* symbol histogram / cursors */
         k.sw_cand = wb2; wb2 += k.dc_max * NB_SYND_CAND * 4;
-        k.sw_rows = wb2; wb2 += std::max(4096, align_up(4 * k.S, 16));                   /* syndromes by configuration, then the 4 output rows */
+        k.sw_rows = wb2; wb2 += align_up(4 * k.S, 16);                                   /* region A: syndromes by configuration, then the sorted keys */
         k.sw_M = wb2; wb2 += align_up(257 * 2, 16);
         k.sw_perm = wb2; wb2 += NB_SYND_PERM_BYTES;
         k.wb_bytes = align_up(wb2, 16);

@@ -34,15 +34,16 @@
 /* a warp's shared memory for the syndrome check node, by shared-window address */
 struct SyndMem {
     uint32_t lists;      /* dc lists: n_m f32 | n_m u8 (stride lstride) in ORIGINAL edge order                          */
-    uint32_t gkey;       /* [S] u32 syndrome LLR bits, grouped by symbol, every group ascending in (LLR, configuration)  */
-    uint32_t gpay;       /* [S] u16 configuration index of the same entries                                               */
-    uint32_t gfa;        /* [S] u8 syndrome symbol by configuration index                                                 */
+    uint32_t keya;       /* region A: [S] u32 syndrome LLR bits by configuration index; after the scatter the same bytes   */
+    uint32_t skey;       /*   hold the keys grouped by symbol, every group ascending (written out of place by the sort)    */
+    uint32_t gkey;       /* region B: [S] u32 keys grouped by symbol, any order inside a group (scatter); before that the   */
+    uint32_t hsat;       /*   [ceil(dc/2)][256] u32 per-bin counts of the decorrelated syndromes, two edges per word (16+16 */
+    uint32_t rows;       /*   bits); after the sort 4 output rows of 256 f32 (indexed by binary image)                      */
+    uint32_t gpay;       /* [S] u16 payload of the grouped keys: decorrelation mask (cfgmask) | symbol << 8                */
+    uint32_t gfa;        /* [S] u8 syndrome symbol by configuration index, directly followed by                            */
+    uint32_t hist;       /* [256] u32 symbol histogram / scatter cursors; after the scatter the two hold                   */
+    uint32_t spay;       /*   [S] u16 payloads in sorted order                                                             */
     uint32_t M;          /* [257] u16 first position of every symbol group                                                */
-    uint32_t rows;       /* 4 output rows of 256 f32 (indexed by binary image); before the walk the same bytes hold        */
-    uint32_t keya;       /*   [S] u32 syndrome LLR bits by configuration index                                             */
-    uint32_t hist;       /* [256] u32 symbol histogram / scatter cursors                                                   */
-    uint32_t hsat;       /* [ceil(dc/2)][256] u32 per-bin counts of the decorrelated syndromes, two edges per word (16+16
-                            bits); the same bytes as gkey, which is only written once the saturation bins are known        */
     uint32_t cand;       /* [dc][NB_SYND_CAND] u32 candidates of the saturation bins                                       */
     uint32_t perm;       /* [16] i32 original edge at presorted position i | [16] f32 saturation level | [16] i32 saturation bin |
                             [16] i32 syndromes below that bin | [16] i32 candidate counters                                */
@@ -61,11 +62,18 @@ struct SyndMem {
  *   - (double)dif < 0.1 / 0.2 / 1 / 2  ==  dif < 0.1f / 0.2f / 1.0f / 2.0f  (0.1f and 0.2f are the first floats above 0.1, 0.2);
  *   - (float)(c * (double)min) for c = 0.5, 0.75, 0.9375: the double product of a float by a 1-4 bit constant is exact, so its
  *     rounding equals the float product;
- *   - c = 0.825 is not representable: with c1 = (float)c, c2 = (float)(c - c1), p = mn*c1, e = fma(mn, c1, -p) (exact),
- *     t = fma(mn, c2, e), the sum p + t equals (float)(c * (double)mn) for EVERY float mn >= 2^-96 (checked exhaustively over
- *     all 2^31 non-negative floats, scripts/check_bayes_f32.c; below 2^-96 e or t underflow, 0 is exact again): that range
- *     keeps the double multiplication behind a branch no real message takes.
- * Branch-free otherwise: divergence would cost more than the few extra instructions. */
+ *   - c = 0.825 is not representable: with c1 = (float)c, c2 = (float)(c - c1),  fma(mn, c1, mn * c2)  equals
+ *     (float)(c * (double)mn) for EVERY float mn >= 2^-96 and for 0 (checked exhaustively over all 2^31 non-negative floats,
+ *     scripts/check_bayes_f32.c; below 2^-96 the product mn * c2 loses bits to underflow).  synd_prepare proves per check node
+ *     that no operand can fall into (0, 2^-96) -- smallest non-zero syndrome LLR >= 2^-32 and no symbol group longer than 64,
+ *     every bayes() step scales by at least 1/2 -- and the walk then runs without the guard; otherwise the guarded variant
+ *     keeps the double multiplication behind a branch.
+ * Branch-free otherwise: divergence would cost more than the few extra instructions.  An unset value is +inf: bayes(x, +inf)
+ * = 1.0f * x = x, which is what the reference's "first hit sets the LLR" does. */
+__device__ __noinline__ float synd_bayes_tiny(float mn) { return __double2float_rn(__dmul_rn(0.825, (double)mn)); }
+
+/* GUARD = false: the caller has shown that no operand lies in (0, 2^-96) (synd_prepare's return value) */
+template <bool GUARD>
 __device__ __forceinline__ float synd_bayes_sel(float m1, float m2)
 {
     const float mn = fminf(m1, m2), hi = fmaxf(m1, m2);          /* M1 < M2 ? (M1, M2) : (M2, M1); equal values give the same pair */
@@ -73,11 +81,9 @@ __device__ __forceinline__ float synd_bayes_sel(float m1, float m2)
     const float f = dif < 0.1f ? 0.5f : dif < 0.2f ? 0.75f : dif < 2.0f ? 0.9375f : 1.0f;
     const float a = __fmul_rn(f, mn);
     const float c1 = 0x1.a66666p-1f, c2 = 0x1.99999ap-27f;       /* 0.825 = c1 + c2 - 2^-52 */
-    const float p = __fmul_rn(mn, c1);
-    const float e = __fmaf_rn(mn, c1, -p);
-    float b = __fadd_rn(p, __fmaf_rn(mn, c2, e));
-    if (((__float_as_uint(mn) & 0x7fffffffu) - 1u) < 0x0f800000u - 1u) b = __double2float_rn(__dmul_rn(0.825, (double)mn));
-    return (dif >= 0.2f && dif < 1.0f) ? b : a;
+    float b = __fmaf_rn(mn, c1, __fmul_rn(mn, c2));
+    if (GUARD) { if (fabsf(mn) < 0x1p-96f && mn != 0.0f) b = synd_bayes_tiny(mn); }      /* out of line: keeps the f64 multiply off the common path */
+    return (!(dif < 0.2f) && dif < 1.0f) ? b : a;
 }
 
 /* monotone 8-bit quantisation of a non-negative float: 16 bins per octave from 2^-4 upwards (bin 0: below, bin 255: beyond
@@ -109,12 +115,13 @@ __device__ __forceinline__ int synd_lane_group(const SyndMem &sm, int lane)
 }
 
 /*
- * Everything up to the walk.  On return: gkey/gpay hold the syndromes grouped by symbol, every group in the reference's
+ * Everything up to the walk.  On return: gkey/gmask hold the syndromes grouped by symbol, every group in the reference's
  * sorted order; M[g] the group starts; perm[0..dc) the presorting; perm+64 the dc saturation levels (:195).
  */
-__device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
+__device__ __forceinline__ bool synd_prepare(const SyndMem &sm, int lane)
 {
     const int dc = sm.dc, n_m = sm.n_m, S = sm.S;
+    uint32_t tiny = 0xffffffffu;                     /* smallest (bit pattern - 1) of the syndrome LLRs: 0.0f wraps to the top */
     /* ---- presorting_mvc ---- */
     {
         const int i = lane < dc ? lane : 0;
@@ -159,6 +166,7 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
                 gf ^= lds_u8(lb[j] + 4 * n_m + c);
             }
             const uint32_t bits = __float_as_uint(llr), bin = synd_bin(bits);
+            tiny = min(tiny, bits - 1u);
             sts_u32(sm.keya + 4 * i, bits);
             sts_u8(sm.gfa + i, gf);
             asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(sm.hist + 4 * gf) : "memory");
@@ -179,6 +187,7 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
                 gf ^= lds_u8(list + 4 * n_m + c);
             }
             const uint32_t bits = __float_as_uint(llr), bin = synd_bin(bits);
+            tiny = min(tiny, bits - 1u);
             sts_u32(sm.keya + 4 * i, bits);
             sts_u8(sm.gfa + i, gf);
             asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(sm.hist + 4 * gf) : "memory");
@@ -190,10 +199,11 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
     }
     __syncwarp();
     /* ---- group starts: exclusive prefix sum over the 256 symbol bins, lane owns bins 8*lane .. 8*lane+7 ---- */
+    uint32_t gmax = 0;                               /* longest symbol group */
     {
         uint32_t h[8], tot = 0;
 #pragma unroll
-        for (int b = 0; b < 8; b++) { h[b] = lds_u32(sm.hist + 4 * (lane * 8 + b)); tot += h[b]; }
+        for (int b = 0; b < 8; b++) { h[b] = lds_u32(sm.hist + 4 * (lane * 8 + b)); tot += h[b]; gmax = max(gmax, h[b]); }
         uint32_t inc = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(NB_FULL, inc, o); if (lane >= o) inc += t; }
@@ -245,7 +255,7 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
             uint32_t pos;
             asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(sm.hist + 4 * gf) : "memory");
             sts_u32(sm.gkey + 4 * pos, key);
-            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * pos), "h"((unsigned short)i) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * pos), "h"((unsigned short)(mem | (gf << 8))) : "memory");
             const uint32_t bin4 = synd_bin(key) * 0x01010101u;
             /* byte d of eq is 0xff where the syndrome's bin is edge d's saturation bin */
             uint32_t hit = (__vcmpeq4(bin4, sb0) & 0x08040201u);
@@ -294,63 +304,64 @@ __device__ __forceinline__ void synd_prepare(const SyndMem &sm, int lane)
         }
     }
     __syncwarp();
-    /* ---- order every symbol group by (LLR, configuration): every lane a run of whole groups of about S/32 entries, ONE
-     * flat loop over the run's entries (insertion towards the start of the entry's own group) so that the lanes' different
-     * group sizes do not serialise ---- */
+    /* ---- order every symbol group by LLR, out of place (gkey/gpay -> skey/spay; region A is free since the scatter, gfa and
+     * the cursors too): the rank of an entry inside its group is the number of members before it in (LLR, position) order.
+     * Every entry is independent of every other -- lane L takes entries L, L+32, ...; the loads of a group's members do
+     * not depend on each other, unlike the steps of an insertion sort ---- */
     {
-        const int gfirst = synd_lane_group(sm, lane);
-        int glast = __shfl_down_sync(NB_FULL, gfirst, 1);
-        if (lane == 31) glast = 256;
-        const int lo = (int)synd_M(sm, (uint32_t)gfirst), hi_i = (int)synd_M(sm, (uint32_t)glast);
-        uint32_t gcur = (uint32_t)gfirst;
-        int gs = lo, gend = (int)synd_M(sm, gcur + 1u);
 #pragma unroll 1
-        for (int i = lo; i < hi_i; i++) {
-            while (i >= gend) { gcur++; gs = gend; gend = (int)synd_M(sm, gcur + 1u); }
+        for (int i = lane; i < S; i += 32) {
             const uint32_t k = lds_u32(sm.gkey + 4 * i);
-            unsigned short p;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p) : "r"(sm.gpay + 2 * i));
-            int j = i - 1;
-            while (j >= gs) {
-                const uint32_t kj = lds_u32(sm.gkey + 4 * j);
-                unsigned short pj;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pj) : "r"(sm.gpay + 2 * j));
-                if (!(kj > k || (kj == k && pj > p))) break;
-                sts_u32(sm.gkey + 4 * (j + 1), kj);
-                asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * (j + 1)), "h"(pj) : "memory");
-                j--;
+            unsigned short pay;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pay) : "r"(sm.gpay + 2 * i));
+            const uint32_t g = (uint32_t)pay >> 8;
+            const int gs = (int)synd_M(sm, g), ge = (int)synd_M(sm, g + 1u);
+            const unsigned long long me = ((unsigned long long)k << 32) | (uint32_t)i;
+            int rank = gs;
+#pragma unroll 1
+            for (int j0 = gs; j0 < ge; j0 += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {                    /* region B extends 16 bytes past its S keys */
+                    const int j = j0 + u;
+                    const unsigned long long other = ((unsigned long long)lds_u32(sm.gkey + 4 * j) << 32) | (uint32_t)j;
+                    rank += (j < ge && other < me) ? 1 : 0;
+                }
             }
-            if (j != i - 1) {
-                sts_u32(sm.gkey + 4 * (j + 1), k);
-                asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.gpay + 2 * (j + 1)), "h"(p) : "memory");
-            }
+            sts_u32(sm.skey + 4 * rank, k);
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sm.spay + 2 * rank), "h"(pay) : "memory");
         }
     }
     __syncwarp();
+    /* bayes() may run without its small-operand guard (see synd_bayes_sel) */
+    tiny = __reduce_min_sync(NB_FULL, tiny);
+    gmax = __reduce_max_sync(NB_FULL, gmax);
+    return tiny >= 0x2f800000u - 1u && gmax <= 64u;            /* 0x2f800000 = 2^-32 */
 }
 
 /* step 4 for the presorted positions d0 .. d0+nd-1 (nd <= 4) in ONE walk: on return out_k[256] = sm.rows + 1024 k
  * (f32, indexed by the binary image of the rotated symbol) holds M_CtoV_LLR[d0+k][.] after saturation
  * (syndrome_decoder.c:93-209).  The reference walks the sorted syndromes and, per symbol, lets the first hit set the LLR
  * and every later hit go through bayes(); hits of different symbols do not interact, so every lane replays the syndromes of
- * its run of symbol groups (contiguous in the symbol-grouped order, ascending inside a group) for all nd edges at once and
- * scatters the results to the symbols (group ^ best symbol of the edge). */
+ * a run of whole symbol groups (contiguous in the symbol-grouped order, ascending inside a group, about S/32 entries) for
+ * all nd edges at once and scatters the results to the symbols (group ^ best symbol of the edge).
+ * GUARD: see synd_bayes_sel; synd_prepare's return value says whether it can be dropped. */
+template <bool GUARD>
 __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, float offset, int lane)
 {
     uint32_t x[4]; float sat[4], hi[4], m[4];
+    const float unset_m = __int_as_float(0x7f800000);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int d = d0 + (k < nd ? k : 0);
         x[k] = lds_u8(sm.lists + lds_u32(sm.perm + 4 * d) * sm.lstride + 4 * sm.n_m);        /* M_VtoC_GF[d][0], :103 */
         sat[k] = lds_f32(sm.perm + 64 + 4 * d);
         hi[k] = __fadd_rn(sat[k], offset);
-        m[k] = 0.0f;
+        m[k] = unset_m;
     }
     const int gfirst = synd_lane_group(sm, lane);
     int glast = __shfl_down_sync(NB_FULL, gfirst, 1);
     if (lane == 31) glast = 256;
     const int lo = (int)synd_M(sm, (uint32_t)gfirst), hi_i = (int)synd_M(sm, (uint32_t)glast);
-    __syncwarp();
 #pragma unroll
     for (int k = 0; k < 4; k++)                                  /* symbols without a hit keep the initial 1500.0 (:131), which the saturation (:198-209) turns into sat + offset unless sat >= 1500 */
         if (k < nd) {
@@ -360,27 +371,29 @@ __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, flo
         }
     __syncwarp();
     const uint32_t ndmask = (1u << nd) - 1u;
-    uint32_t have = 0u, gcur = (uint32_t)gfirst;
-    int gend = (int)synd_M(sm, gcur + 1u);                       /* end of group gcur in the grouped order */
+    /* one entry ahead: the next entry's symbol also tells whether this one closes its group */
+    float llr = __uint_as_float(lds_u32(sm.skey + 4 * min(lo, sm.S - 1)));
+    uint32_t pay = lds_u16(sm.spay + 2 * min(lo, sm.S - 1));
+#pragma unroll 1
     for (int i = lo; i < hi_i; i++) {
-        while (i >= gend) { gcur++; gend = (int)synd_M(sm, gcur + 1u); }    /* empty groups are skipped; i < M[glast] bounds gcur */
-        unsigned short ps;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ps) : "r"(sm.gpay + 2 * i));
-        const float llr = __uint_as_float(lds_u32(sm.gkey + 4 * i));
-        const uint32_t mem = (lds_u8(sm.cfgmask + (uint32_t)ps) >> d0) & ndmask;       /* decorrelation, :96-98 */
+        const int nx = min(i + 1, sm.S - 1);
+        const float llr_n = __uint_as_float(lds_u32(sm.skey + 4 * nx));
+        const uint32_t pay_n = lds_u16(sm.spay + 2 * nx);
+        const uint32_t mem = (pay >> d0) & ndmask;               /* decorrelation, :96-98 */
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float nb = synd_bayes_sel(llr, m[k]);
-            const float first = ((have >> k) & 1u) ? nb : llr;
-            m[k] = ((mem >> k) & 1u) ? first : m[k];
+            const float nb = synd_bayes_sel<GUARD>(llr, m[k]);
+            m[k] = ((mem >> k) & 1u) ? nb : m[k];
         }
-        have |= mem;
-        if (i + 1 == gend) {                                     /* last syndrome of the symbol: saturation (:198-209) and store */
+        if (i + 1 == hi_i || ((pay ^ pay_n) >> 8) != 0u) {       /* last syndrome of the symbol: saturation (:198-209) and store */
+            const uint32_t g = pay >> 8;
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                if ((have >> k) & 1u) sts_f32(sm.rows + 1024 * k + 4 * ((gcur ^ x[k]) & 255u), m[k] > sat[k] ? hi[k] : m[k]);
-            have = 0u;
+            for (int k = 0; k < 4; k++) {
+                if (m[k] < unset_m) sts_f32(sm.rows + 1024 * k + 4 * ((g ^ x[k]) & 255u), m[k] > sat[k] ? hi[k] : m[k]);
+                m[k] = unset_m;
+            }
         }
+        llr = llr_n; pay = pay_n;
     }
     __syncwarp();
 }

@@ -1,6 +1,6 @@
 /*
  * check_bayes_f32.c -- exhaustive check of the f32 restatement of  (float)(0.825 * (double)m)  used by synd_bayes_sel
- * (csrc/nbldpc_synd.cuh): over ALL non-negative finite floats m, the formula  p + fma(m, c2, fma(m, c1, -p)),  p = m * c1,
+ * (csrc/nbldpc_synd.cuh): over ALL non-negative finite floats m, the formula  fma(m, c1, m * c2)  with c1 = (float)0.825, c2 = (float)(0.825 - c1)
  * must give the reference's bits for every m >= 2^-96 (and for 0); the kernel keeps the double multiplication below that.
  *
  *   gcc -O2 -fopenmp -ffp-contract=off -o /tmp/check_bayes_f32 scripts/check_bayes_f32.c -lm && /tmp/check_bayes_f32
@@ -24,7 +24,7 @@ int main(void)
     for (long u = 0; u < 0x7f800000L; u++) {
         const float m = u2f((uint32_t)u);
         const float ref = (float)(c * (double)m);
-        const float p = m * c1, e = fmaf(m, c1, -p), r = p + fmaf(m, c2, e);
+        const float r = fmaf(m, c1, m * c2);
         if (memcmp(&r, &ref, 4)) { if ((uint32_t)u >= threshold || u == 0) bad_above++; else bad_below++; }
     }
     printf("mismatches: %ld at m = 0 or m >= 2^-96 (must be 0), %ld below (handled in f64 by the kernel)\n", bad_above, bad_below);

@@ -144,3 +144,46 @@ def test_adversarial_llr_inputs_equal_oracle(seed, tmp_path):
             app, ctov = d.get_state(f)
             assert np.array_equal(app, r["app"], equal_nan=True) and np.array_equal(ctov, r["ctov"], equal_nan=True), (seed, f)
     o.close(); d.close()
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_syndrome_node_with_tiny_and_tied_llrs_equals_oracle(seed, tmp_path):
+    """The syndrome check node drops the small-operand guard of bayes() only when it can prove that no operand falls below 2^-96
+    (synd_prepare): LLRs scaled down to 2^-40 .. 2^-110 (and exact ties, which make long symbol groups) must take the guarded walk
+    and still equal the reference bit for bit."""
+    rng = np.random.default_rng(7000 + seed)
+    q = int(rng.choice([16, 64, 256]))
+    dc = int(rng.choice([4, 4, 5]))
+    dcs = [dc] * int(rng.integers(3, 7))
+    N = max(dc + 2, len(dcs) + 2, sum(dcs) // 2)
+    a = _random_code(rng, q, N, dcs)
+    path = str(tmp_path / "code.alist")
+    write_alist_ubs(path, a)
+    code = nbldpc.Code(path)
+    o = ol.Oracle(path, code.dialect)
+    n_m = int(rng.integers(6, min(q, 20) + 1))
+    d1, d2, d3 = int(rng.integers(2, n_m)), int(rng.integers(1, min(n_m, 6))), int(rng.integers(1, min(n_m, 4)))
+    trunc = 1000 if nbldpc.config_table(dc, d1, d2, d3, 0).shape[0] > 1024 else 0
+    cfg = o.build_config_table(dc, d1, d2, d3, trunc)
+    kept = min(int((cfg[:, d] == 0).sum()) - 3 * d for d in range(dc))
+    if kept < 2:
+        pytest.skip("no admissible n_cv for this table")
+    n_cv = int(rng.integers(1, max(2, min(kept, 20))))
+    frames = 6
+    kind = seed % 3
+    if kind == 0:
+        llr = (rng.random((frames, N, q)) * 30).astype(np.float32) * np.float32(2.0 ** -int(rng.integers(40, 111)))
+    elif kind == 1:
+        llr = rng.integers(0, 4, (frames, N, q)).astype(np.float32)                        # ties everywhere
+    else:
+        llr = (rng.random((frames, N, q)) * 30).astype(np.float32)
+        llr[rng.random(llr.shape) < 0.3] *= np.float32(2.0 ** -100)                         # a mix of ordinary and tiny values
+    d = nbldpc.Decoder(code, n_m, 20, 4, 0.3, max_batch=frames, ecn_kind=1, d1=d1, d2=d2, d3=d3, cfg_trunc=trunc, n_cv=n_cv)
+    dec, synd, it = d.decode_llr(llr)
+    for f in range(frames):
+        r = o.decode_frame(llr[f], n_m, 20, 4, 0.3, want_state=(f < 2), ecn=1, cfg=cfg, n_cv=n_cv)
+        assert (dec[f] == r["decide"]).all() and synd[f] == r["synd"] and it[f] == r["iters"], (seed, f)
+        if f < 2:
+            app, ctov = d.get_state(f)
+            assert app.tobytes() == r["app"].tobytes() and ctov.tobytes() == r["ctov"].tobytes(), (seed, f)
+    o.close(); d.close()
