@@ -315,12 +315,12 @@ __device__ __forceinline__ void load_cfg_table(unsigned char *smem, const KArgs 
 /* dense output row of one edge from the syndrome check node: Mcv[s] = M[img(MULGF[s][h])] (syndrome_decoder.c:260-266
  * followed by the scatter NB_LDPC.c:415-421) */
 template <int Q, bool CLOSED>
-__device__ __forceinline__ void synd_dense_row(uint32_t out, const GFTab &gf, int h, int lane, float (&mcv)[QTraits<Q>::VPL])
+__device__ __forceinline__ void synd_dense_row(uint32_t out, const GFTab &gf, int h, int lane, float sat, float hi, float (&mcv)[QTraits<Q>::VPL])
 {
 #pragma unroll
     for (int j = 0; j < QTraits<Q>::VPL; j++) {
         const int s = QTraits<Q>::sym(lane, j);
-        mcv[j] = (Q >= 32 || lane < Q) ? lds_f32(out + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)) : NB_SENT;
+        mcv[j] = (Q >= 32 || lane < Q) ? synd_saturate(lds_f32(out + 4 * gf_rot_in<Q, CLOSED>(gf, s, h)), sat, hi) : NB_SENT;
     }
 }
 
@@ -777,14 +777,15 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                         __syncwarp();
                         const bool plain = synd_prepare(sm, lane);
                         for (int d = 0; d < dc; d++) {
-                            if ((d & 3) == 0) { if (plain) synd_walk<false>(sm, d, min(4, dc - d), a.offset, lane); else synd_walk<true>(sm, d, min(4, dc - d), a.offset, lane); }
+                            if ((d & 3) == 0) { if (plain) synd_walk<false>(sm, d, min(4, dc - d), lane); else synd_walk<true>(sm, d, min(4, dc - d), lane); }
                             const uint32_t out = sm.rows + 1024 * (d & 3);
                             const int t = (int)lds_u32(sm.perm + 4 * d);                   /* un-permute, syndrome_decoder.c:234-253 */
                             const uint32_t ei = wm.ew[c * dcm + t];
                             const uint32_t var = ei & 0xfffffu;
                             float *cdrow = cd0 + (size_t)((uint32_t)t * (uint32_t)Q);
                             float mcv[VPL], v[VPL], cv[VPL];
-                            synd_dense_row<Q, CLOSED>(out, gf, (ei >> 20) & 0xff, lane, mcv);
+                            const float sat = lds_f32(sm.perm + 64 + 4 * d);
+                            synd_dense_row<Q, CLOSED>(out, gf, (ei >> 20) & 0xff, lane, sat, __fadd_rn(sat, a.offset), mcv);
                             load_row<Q>(app_f + (size_t)(var * (uint32_t)Q), lane, v);
                             load_row<Q>(cdrow, lane, cv);
 #pragma unroll
@@ -949,13 +950,14 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_synd_kernel(const KArgs a
         __syncwarp();
         const bool plain = synd_prepare(sm, lane);
         for (int d = 0; d < dc; d++) {
-            if ((d & 3) == 0) { if (plain) synd_walk<false>(sm, d, min(4, dc - d), a.offset, lane); else synd_walk<true>(sm, d, min(4, dc - d), a.offset, lane); }
+            if ((d & 3) == 0) { if (plain) synd_walk<false>(sm, d, min(4, dc - d), lane); else synd_walk<true>(sm, d, min(4, dc - d), lane); }
             const uint32_t out = sm.rows + 1024 * (d & 3);
             const int t = (int)lds_u32(sm.perm + 4 * d);
             float *dst = cllr + ((size_t)b * dc + t) * Q;
             int *gdst = cgf + ((size_t)b * dc + t) * Q;
+            const float sat = lds_f32(sm.perm + 64 + 4 * d), hi = __fadd_rn(sat, a.offset);
             for (int k = lane; k < Q; k += 32) {
-                dst[k] = lds_f32(out + 4 * gf.img[k]);
+                dst[k] = synd_saturate(lds_f32(out + 4 * gf.img[k]), sat, hi);
                 gdst[k] = gf_rot_out<Q, CLOSED>(gf, gf.img[k], a.hval[e0 + t]);
             }
             __syncwarp();

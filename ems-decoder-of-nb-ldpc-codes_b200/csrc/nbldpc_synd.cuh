@@ -339,23 +339,26 @@ __device__ __forceinline__ bool synd_prepare(const SyndMem &sm, int lane)
 }
 
 /* step 4 for the presorted positions d0 .. d0+nd-1 (nd <= 4) in ONE walk: on return out_k[256] = sm.rows + 1024 k
- * (f32, indexed by the binary image of the rotated symbol) holds M_CtoV_LLR[d0+k][.] after saturation
- * (syndrome_decoder.c:93-209).  The reference walks the sorted syndromes and, per symbol, lets the first hit set the LLR
+ * (f32, indexed by the binary image of the rotated symbol) holds M_CtoV_LLR[d0+k][.] BEFORE the saturation of
+ * syndrome_decoder.c:198-209, which the reader of the row applies (synd_saturate: 8 values per lane and edge instead of one
+ * per lane and walk step).  The reference walks the sorted syndromes and, per symbol, lets the first hit set the LLR
  * and every later hit go through bayes(); hits of different symbols do not interact, so every lane replays the syndromes of
  * a run of whole symbol groups (contiguous in the symbol-grouped order, ascending inside a group, about S/32 entries) for
  * all nd edges at once and scatters the results to the symbols (group ^ best symbol of the edge).
  * GUARD: see synd_bayes_sel; synd_prepare's return value says whether it can be dropped. */
+/* saturation of one output value (syndrome_decoder.c:198-209): above the level of edge d -> level + offset; symbols no syndrome
+ * reached still hold the initial 1500.0 and take the same test */
+__device__ __forceinline__ float synd_saturate(float v, float sat, float hi) { return v > sat ? hi : v; }
+
 template <bool GUARD>
-__device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, float offset, int lane)
+__device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, int lane)
 {
-    uint32_t x[4]; float sat[4], hi[4], m[4];
+    uint32_t xs[4]; float m[4];
     const float unset_m = __int_as_float(0x7f800000);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int d = d0 + (k < nd ? k : 0);
-        x[k] = lds_u8(sm.lists + lds_u32(sm.perm + 4 * d) * sm.lstride + 4 * sm.n_m);        /* M_VtoC_GF[d][0], :103 */
-        sat[k] = lds_f32(sm.perm + 64 + 4 * d);
-        hi[k] = __fadd_rn(sat[k], offset);
+        xs[k] = lds_u8(sm.lists + lds_u32(sm.perm + 4 * d) * sm.lstride + 4 * sm.n_m) << 2;  /* M_VtoC_GF[d][0], :103 */
         m[k] = unset_m;
     }
     const int gfirst = synd_lane_group(sm, lane);
@@ -363,10 +366,10 @@ __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, flo
     if (lane == 31) glast = 256;
     const int lo = (int)synd_M(sm, (uint32_t)gfirst), hi_i = (int)synd_M(sm, (uint32_t)glast);
 #pragma unroll
-    for (int k = 0; k < 4; k++)                                  /* symbols without a hit keep the initial 1500.0 (:131), which the saturation (:198-209) turns into sat + offset unless sat >= 1500 */
+    for (int k = 0; k < 4; k++)                                  /* symbols without a hit keep the initial 1500.0 (:131) */
         if (k < nd) {
             const uint32_t a = sm.rows + 1024 * k + lane * 16;
-            const float unset = 1500.0f > sat[k] ? hi[k] : 1500.0f;
+            const float unset = 1500.0f;
             asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n\tst.shared.v4.f32 [%0+512], {%1, %1, %1, %1};" :: "r"(a), "f"(unset) : "memory");
         }
     __syncwarp();
@@ -385,11 +388,11 @@ __device__ __forceinline__ void synd_walk(const SyndMem &sm, int d0, int nd, flo
             const float nb = synd_bayes_sel<GUARD>(llr, m[k]);
             m[k] = ((mem >> k) & 1u) ? nb : m[k];
         }
-        if (i + 1 == hi_i || ((pay ^ pay_n) >> 8) != 0u) {       /* last syndrome of the symbol: saturation (:198-209) and store */
-            const uint32_t g = pay >> 8;
+        if (i + 1 == hi_i || ((pay ^ pay_n) >> 8) != 0u) {       /* last syndrome of the symbol: store */
+            const uint32_t g4 = (pay >> 8) << 2;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (m[k] < unset_m) sts_f32(sm.rows + 1024 * k + 4 * ((g ^ x[k]) & 255u), m[k] > sat[k] ? hi[k] : m[k]);
+                if (m[k] < unset_m) sts_f32(sm.rows + 1024 * k + (g4 ^ xs[k]), m[k]);
                 m[k] = unset_m;
             }
         }
