@@ -607,6 +607,7 @@ __device__ __forceinline__ int es_serial(uint32_t l1, uint32_t s1, int len1, uin
 {
     float bv[8];
     unsigned long long seen = 0ull;
+    uint32_t seen32 = 0u;                                  /* q <= 32: one word */
     if constexpr (Q > 64) {
 #pragma unroll
         for (int w = 0; w < Q / 32; w++) sts_u32(mask + w * 128, 0u);
@@ -646,9 +647,13 @@ __device__ __forceinline__ int es_serial(uint32_t l1, uint32_t s1, int len1, uin
             const uint32_t w = lds_u32(wa), bit = 1u << (g & 31);
             fresh = !(w & bit);
             if (fresh) sts_u32(wa, w | bit);
-        } else {
+        } else if constexpr (Q > 32) {
             fresh = !((seen >> g) & 1ull);
             seen |= 1ull << g;
+        } else {
+            const uint32_t bit = 1u << g;
+            fresh = !(seen32 & bit);
+            seen32 |= bit;
         }
         if (fresh) { sts_f32(lo + 4 * s, val); sts_u8(so + s, g); s++; }     /* :490-496 */
         if (s == n_m) break;                                                /* :502 */
