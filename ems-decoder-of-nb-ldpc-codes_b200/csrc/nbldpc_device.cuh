@@ -333,6 +333,9 @@ template <int Q> __device__ __forceinline__ int warp_argmin(const float (&v)[QTr
 #ifndef NB_SEL_CAPTURE
 #define NB_SEL_CAPTURE 1
 #endif
+#ifndef NB_SEL_UNROLL
+#define NB_SEL_UNROLL 1        /* n_m = 20 and n_m = 16: all reduction rounds straight-line */
+#endif
 #ifndef NB_SEL_LOOKAHEAD
 #define NB_SEL_LOOKAHEAD 0     /* capture mode only; measured: no gain (226.7 vs 226.4 Mbit/s), one instruction more per round */
 #endif
@@ -454,6 +457,20 @@ __device__ __forceinline__ void select_edges(const float (&mvc)[NEDG][QTraits<Q>
     const int full = rounds - 1;
     int r = 0;
     int lr = lane;                                    /* lane - r: lane r keeps the minimum of round r */
+#if NB_SEL_UNROLL && !NB_SEL_LOOKAHEAD
+    /* the usual list lengths straight-line: the rolled loop below spends 13 of its 61 instructions per four rounds on
+     * loop-carried register moves, the convergence check in front of the first REDUX and the counter */
+#define NB_SEL_ROUNDS4(A, B, C, D)                                      \
+    _Pragma("unroll") for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, A); \
+    _Pragma("unroll") for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, B); \
+    _Pragma("unroll") for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, C); \
+    _Pragma("unroll") for (int e = 0; e < NEDG; e++) NB_SEL_ROUND(e, D);
+    if (full == 20 || full == 16) {
+        NB_SEL_ROUNDS4(0, 1, 2, 3) NB_SEL_ROUNDS4(4, 5, 6, 7) NB_SEL_ROUNDS4(8, 9, 10, 11) NB_SEL_ROUNDS4(12, 13, 14, 15)
+        if (full == 20) { NB_SEL_ROUNDS4(16, 17, 18, 19) }
+        r = full; lr = lane - full;
+    }
+#endif
 #pragma unroll 1
     for (; r + 4 <= full; r += 4) {                   /* n_m = 20 or 16 full rounds: no remainder */
 #pragma unroll
