@@ -236,7 +236,7 @@ def reference_arm(args, rank, world):
             "config": config_dict(wl, code, fpp * cores, "host CPU only", args.ecn),
             "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(wl, code, frames, note, ecn="bubble"):
@@ -470,8 +470,6 @@ def ours(args, rank, local_rank, world):
     import nbldpc
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout, next to the JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -517,7 +515,7 @@ def ours(args, rank, local_rank, world):
                             "headline leg (same steps and warm-up); `bench.py --ecn %s` makes it the headline" % (
                                 ("388", "392", "syndrome") if legs[1] == "syndrome" else ("392", "388", "bubble"))
             line["config5_as_written" if (legs[1] == "syndrome" and BASELINE_CONFIG.get(wl) == 5) else "other_check_node"] = other
-        print(json.dumps(line), flush=True)
+        emit(line)
     nbldpc.unpin(noisy)
     for o in out:
         nbldpc.unpin(o)
@@ -528,6 +526,28 @@ def ours(args, rank, local_rank, world):
 def code_bits(code, syms):
     b = code.tables()[0]
     return b[syms]
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded later write there too (NCCL prints its version banner on stdout
+    when NCCL_DEBUG is VERSION or WARN): from here on file descriptor 1 is stderr for everybody, and emit() alone writes to the
+    real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -549,10 +569,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl == "ours" and world == 1 and args.gpus > 1):           # (the torchrun relaunch below keeps its children's stdout)
+        claim_stdout()
     if args.impl == "reference":
         if args.workload in NO_REFERENCE:
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "the reference's LoadCode cannot read the full-alist file of workload %s" % args.workload}))
+                emit({"impl": "reference", "unavailable": "the reference's LoadCode cannot read the full-alist file of workload %s" % args.workload})
             return
         reference_arm(args, rank, world)
         return

@@ -1,8 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-export NO_NCU=1
-bash scripts/gpu_variants.sh AD_64800_R12_GF256 2368 "default"
-bash scripts/gpu_variants.sh AD_64800_R12_GF256 592 "default" --ecn syndrome
-bash scripts/gpu_variants.sh MatDeclercq_R12_GF64 4096 "default"
-bash scripts/gpu_variants.sh Mat24_N480_M240 65536 "default"
-bash scripts/gpu_variants.sh KN_64800_R34_GF256 2368 "default"
+nvidia-smi -L | head -8
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_8gpu.json')); print('8GPU value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'sim', d['simulation'] and round(d['simulation']['value'],1), 'synd', round(d['config5_as_written']['value'],1), 'n_gpus', d['n_gpus'], 'sharding_check', d.get('sharding_check'))"
+timeout 600 python -m pytest tests -m gpu -q -k "several_devices or multi_gpu or two_gpus" 2>&1 | tail -3
