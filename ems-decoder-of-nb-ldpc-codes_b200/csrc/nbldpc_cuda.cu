@@ -81,6 +81,8 @@ struct KArgs {
     int rec_stride;
     int *out_decide, *out_synd, *out_iters, *frame_slot, *slot_frame;
     unsigned *queue, *slow_counter;
+    const unsigned *ready;   /* streamed input (decode_host): frames copied to the device so far; nullptr = the whole batch is resident */
+    unsigned *fault;         /* set when a CTA gave up waiting for its frames */
     /* shared memory map (bytes): tables | misc | per-warp scratch areas | per-warp lists */
     int off_tab, off_misc, off_wa, wa_bytes, off_wb, wb_bytes;
     int wa_mask, wa_meta, wa_einfo, wa_len;   /* offsets inside a warp's small private area: ES mask | tile meta | tile edge words | list lengths */
@@ -655,6 +657,21 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
         const int base = *s_base;
         if (base >= a.B) break;
         const int nf = min(F, a.B - base);
+        if (a.ready) {
+            /* the host is still copying the batch in (frame order, a counter after every piece): wait for this group's frames.
+             * Copies run ~25x faster than the decoder consumes them, so only the first groups of a launch ever wait. */
+            if (tid == 0) {
+                const unsigned need = (unsigned)(base + nf);
+                unsigned have, spins = 0;
+                for (;;) {
+                    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(have) : "l"(a.ready) : "memory");
+                    if (have >= need) break;
+                    if (++spins > (1u << 23)) { atomicExch(a.fault, 1u); break; }        /* ~4 s: the copy never came */
+                    __nanosleep(500);
+                }
+            }
+            __syncthreads();
+        }
         /* ---------------- frame initialisation: NB_LDPC.c:273-288 + channel.c:66-76 ---------------- */
         for (int w = warp; w < nf * N; w += nw) {
             const int f = w / N, n = w - f * N;
@@ -1059,7 +1076,7 @@ static const void *checknode_fn(int q, int closed, int ecn)
 struct nbgpu_ctx {
     int device;
     cudaStream_t stream, copy_stream;        /* kernels | host<->device copies of the chunked end-to-end path */
-    cudaEvent_t ev0, ev1, ev_t0, ev_t1, ev_h2d[4], ev_k[4];
+    cudaEvent_t ev0, ev1, ev_t0, ev_t1, ev_h2d[1];
     int per_sm;
     nbgpu_params p;
     KArgs k;
@@ -1076,7 +1093,8 @@ struct nbgpu_ctx {
     float *d_app; uint8_t *d_ctov; uint8_t *d_dec;
     float *d_in; size_t in_capacity;
     int *d_decide, *d_synd, *d_iters, *d_frame_slot, *d_slot_frame;
-    unsigned *d_queue, *d_slow;
+    unsigned *d_queue, *d_slow, *d_ready, *d_fault;
+    unsigned *h_ready;                       /* pinned: cumulative frame counts of the input pieces of decode_host */
     int resident_B, resident_kind;
     /* device frame source (nbldpc_source.cuh), set up by the first nbgpu_source_frames */
     struct {
@@ -1212,7 +1230,7 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     if (prop.major < 10) { ctx_err(c, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); nbgpu_destroy(c); return NBGPU_ECUDA; }
     CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKF(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; i++) { CKF(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming)); CKF(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)); }
+    CKF(cudaEventCreateWithFlags(&c->ev_h2d[0], cudaEventDisableTiming));
     CKF(cudaEventCreate(&c->ev0)); CKF(cudaEventCreate(&c->ev1));
     CKF(cudaEventCreate(&c->ev_t0)); CKF(cudaEventCreate(&c->ev_t1));
 
@@ -1383,12 +1401,14 @@ extern "C" int nbgpu_create(nbgpu_ctx **out, const nbgpu_code *code, const nbgpu
     CKF(cudaMalloc((void **)&c->d_frame_slot, (size_t)max_batch * sizeof(int)));
     CKF(cudaMalloc((void **)&c->d_slot_frame, (size_t)c->nslots * sizeof(int)));
     CKF(cudaMemset(c->d_slot_frame, 0xff, (size_t)c->nslots * sizeof(int)));
-    CKF(cudaMalloc((void **)&c->d_queue, 8 * sizeof(unsigned)));       /* [0..3] work queues of up to 4 chunks, [4] slow-path counter */
-    c->d_slow = c->d_queue + 4;
+    CKF(cudaMalloc((void **)&c->d_queue, 8 * sizeof(unsigned)));       /* [0] work queue, [4] slow-path counter, [5] frames copied in so far (decode_host), [6] fault flag */
+    c->d_slow = c->d_queue + 4; c->d_ready = c->d_queue + 5; c->d_fault = c->d_queue + 6;
     CKF(cudaMemset(c->d_queue, 0, 8 * sizeof(unsigned)));
+    CKF(cudaHostAlloc((void **)&c->h_ready, 16 * sizeof(unsigned), cudaHostAllocDefault));
     k.app = c->d_app; k.ctov = c->d_ctov; k.dec = c->d_dec; k.ctov_dense = c->d_ctov_dense;
     k.out_decide = c->d_decide; k.out_synd = c->d_synd; k.out_iters = c->d_iters;
     k.frame_slot = c->d_frame_slot; k.slot_frame = c->d_slot_frame; k.queue = c->d_queue; k.slow_counter = c->d_slow;
+    k.ready = nullptr; k.fault = c->d_fault;
     /* the memsets above ran on the legacy stream, the kernels run on c->stream (non-blocking): order them once, here */
     CKF(cudaDeviceSynchronize());
 #undef CKF
@@ -1404,12 +1424,13 @@ extern "C" void nbgpu_destroy(nbgpu_ctx *c)
                      c->d_rotout, c->d_img, c->d_inv, c->d_mod, c->d_app, c->d_ctov, c->d_dec, c->d_in, c->d_decide, c->d_synd,
                      c->d_iters, c->d_frame_slot, c->d_slot_frame, c->d_queue };
     for (void *b : bufs) if (b) cudaFree(b);
+    if (c->h_ready) cudaFreeHost(c->h_ready);
     source_teardown(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
-    for (int i = 0; i < 4; i++) { if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
+    if (c->ev_h2d[0]) cudaEventDestroy(c->ev_h2d[0]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     free(c->row_ptr_h); free(c->inv_h);
@@ -1557,18 +1578,19 @@ extern "C" int nbgpu_download(nbgpu_ctx *c, int *decide, int *synd, int *iters)
     return NBGPU_OK;
 }
 
-/* End-to-end decode of B frames from HOST buffers.  Large batches are cut into up to four chunks so that the H2D copy of
- * chunk i+1 and the D2H copy of chunk i-1 run (on the copy stream) under the kernel of chunk i; every chunk still fills
- * the persistent grid at least twice.  Small batches take the single-launch path (and keep their state readable). */
+/* End-to-end decode of B frames from HOST buffers.  A large batch is decoded by ONE launch that starts as soon as the first
+ * wave of frames is on the device: the input goes over in up to 8 pieces on the copy stream, every piece followed by a 4-byte
+ * copy of the number of frames now present (d_ready), and a CTA that takes frames [base, base+F) from the work queue first
+ * waits until d_ready covers them (decode_kernel, a.ready).  Copies run ~25x faster than the decoder consumes frames, so
+ * only the first groups ever wait and the H2D time disappears behind the kernel -- without cutting the batch into several
+ * launches, whose starts and tails cost as much as the copies they hid (measured: 340 ms either way against 327.6 ms for the
+ * kernel alone on config 5).  Small batches take the plain upload / run / download path (and keep their state readable). */
 static int decode_host(nbgpu_ctx *c, const float *src, size_t per_frame, int kind, int B, int *decide, int *synd, int *iters)
 {
     if (!c || !src) { ctx_err(c, "NULL argument"); return NBGPU_EINVAL; }
     if (B < 1 || B > c->max_batch) { ctx_err(c, "B=%d outside 1..max_batch=%d", B, c->max_batch); return NBGPU_EINVAL; }
     const int wave = c->grid * c->k.F;
-    int nch = B / (2 * wave);
-    nch = nch < 1 ? 1 : nch > 4 ? 4 : nch;
-    if (getenv("NBGPU_NO_CHUNKS")) nch = 1;
-    if (nch == 1) {
+    if (B < 2 * wave || getenv("NBGPU_NO_CHUNKS")) {
         int rc = upload_common(c, src, per_frame, B, kind);
         if (rc || (rc = nbgpu_run(c)) || (rc = nbgpu_download(c, decide, synd, iters))) return rc;
         return NBGPU_OK;
@@ -1577,37 +1599,44 @@ static int decode_host(nbgpu_ctx *c, const float *src, size_t per_frame, int kin
     int rc = ensure_input(c, per_frame * (size_t)B);
     if (rc) return rc;
     c->resident_B = B; c->resident_kind = kind; c->src.state = 0;
-    int lo[5];
-    for (int i = 0; i <= nch; i++) lo[i] = (int)(((long)B * i / nch) / c->k.F * c->k.F);
-    lo[nch] = B;
+    /* pieces: one wave first, the rest in up to 7 equal runs of whole waves */
+    int lo[9], np = 1;
+    {
+        const int W = B / wave, rest = W - 1, runs = rest < 7 ? rest : 7;
+        lo[0] = 0; lo[1] = wave;
+        for (int i = 1; i <= runs; i++) lo[1 + i] = wave + (int)((long)rest * i / runs) * wave;
+        np = 1 + runs;
+        lo[np] = B;
+    }
+    for (int i = 0; i < np; i++) c->h_ready[i] = (unsigned)lo[i + 1];
     CK(c, cudaStreamSynchronize(c->stream));                  /* earlier work on the buffers is done */
-    for (int i = 0; i < nch; i++) {
+    CK(c, cudaMemsetAsync(c->d_ready, 0, 2 * sizeof(unsigned), c->copy_stream));         /* d_ready, d_fault */
+    CK(c, cudaEventRecord(c->ev_h2d[0], c->copy_stream));
+    for (int i = 0; i < np; i++) {
         CK(c, cudaMemcpyAsync(c->d_in + per_frame * lo[i], src + per_frame * lo[i], per_frame * (lo[i + 1] - lo[i]) * sizeof(float),
                               cudaMemcpyHostToDevice, c->copy_stream));
-        CK(c, cudaEventRecord(c->ev_h2d[i], c->copy_stream));
+        CK(c, cudaMemcpyAsync(c->d_ready, c->h_ready + i, sizeof(unsigned), cudaMemcpyHostToDevice, c->copy_stream));
     }
-    CK(c, cudaMemsetAsync(c->d_queue, 0, 4 * sizeof(unsigned), c->stream));
+    KArgs k = c->k;
+    k.B = B; k.input_kind = kind; k.in = c->d_in; k.ready = c->d_ready;
+    CK(c, cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned), c->stream));
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[0], 0));   /* the counter starts at zero */
     CK(c, cudaEventRecord(c->ev0, c->stream));
-    for (int i = 0; i < nch; i++) {
-        KArgs k = c->k;
-        const int n = lo[i + 1] - lo[i];
-        k.B = n; k.input_kind = kind; k.in = c->d_in + per_frame * lo[i];
-        k.out_decide = c->d_decide + (size_t)lo[i] * c->N; k.out_synd = c->d_synd + lo[i]; k.out_iters = c->d_iters + lo[i];
-        k.frame_slot = c->d_frame_slot + lo[i]; k.queue = c->d_queue + i; k.frame0 = lo[i];
-        const int grid = std::min(c->grid, (n + k.F - 1) / k.F);
-        CK(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[i], 0));
+    {
         void *args[] = { (void *)&k };
-        CK(c, cudaLaunchKernel(decode_fn(c->q, k.gf_closed, k.ecn), dim3(grid), dim3(k.nw * 32), args, k.smem_bytes, c->stream));
-        CK(c, cudaEventRecord(c->ev_k[i], c->stream));
-        c->launches += 1;
-        CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_k[i], 0));
-        if (decide) CK(c, cudaMemcpyAsync(decide + (size_t)lo[i] * c->N, c->d_decide + (size_t)lo[i] * c->N, (size_t)n * c->N * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
-        if (synd) CK(c, cudaMemcpyAsync(synd + lo[i], c->d_synd + lo[i], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
-        if (iters) CK(c, cudaMemcpyAsync(iters + lo[i], c->d_iters + lo[i], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(c, cudaLaunchKernel(decode_fn(c->q, k.gf_closed, k.ecn), dim3(c->grid), dim3(k.nw * 32), args, k.smem_bytes, c->stream));
     }
+    CK(c, cudaGetLastError());
     CK(c, cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    unsigned fault = 0;
+    if (decide) CK(c, cudaMemcpyAsync(decide, c->d_decide, (size_t)B * c->N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (synd) CK(c, cudaMemcpyAsync(synd, c->d_synd, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (iters) CK(c, cudaMemcpyAsync(iters, c->d_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&fault, c->d_fault, sizeof fault, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->copy_stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (fault) { ctx_err(c, "decode: the kernel gave up waiting for its input frames (host-to-device copy did not arrive)"); return NBGPU_ECUDA; }
     return NBGPU_OK;
 }
 

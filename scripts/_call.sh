@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L | head -8
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_8gpu.json')); print('8GPU value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'sim', d['simulation'] and round(d['simulation']['value'],1), 'synd', round(d['config5_as_written']['value'],1), 'n_gpus', d['n_gpus'], 'sharding_check', d.get('sharding_check'))"
-timeout 600 python -m pytest tests -m gpu -q -k "several_devices or multi_gpu or two_gpus" 2>&1 | tail -3
+timeout 120 python scripts/e2e_probe.py 2>&1 | tail -10
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 --no-cpu 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('value',round(d['value'],2),'e2e',round(d['e2e']['value'],2), d['e2e']['ms_per_step'], d['roofline']['kernel_ms'], d['clocks']); o=d['config5_as_written']; print('synd',round(o['value'],2),'e2e',round(o['e2e']['value'],2))"
