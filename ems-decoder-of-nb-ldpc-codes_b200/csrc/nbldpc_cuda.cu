@@ -52,9 +52,19 @@
 #define NE 2              /* edges interleaved per warp in phases 1 and 3 */
 #endif
 #ifndef NB_L2_PREFETCH
-#define NB_L2_PREFETCH 1   /* phase 1 pulls the next pair's APP rows and records into L2 while the current pair is selected */
+#define NB_L2_PREFETCH 1   /* phase 1 pulls the next node's APP rows and records into L2 while the current one is selected: 0 never,
+                              1 where it pays (GF(64): two lines per row, little work per row to hide the latency; measured +1.4 % /
+                              +3.3 % on configs 3 / 2, but -0.7 .. -1.3 % on GF(256) and GF(16), where the 24 / 16 warps hide the
+                              latency already and the extra L2 traffic costs board power -- config 5 runs at the 1 kW cap), 2 always */
 #endif
 
+#define NB_PF(Q) (NB_L2_PREFETCH == 2 || (NB_L2_PREFETCH == 1 && (Q) == 64))
+#ifndef NB_P3_PREFETCH
+#define NB_P3_PREFETCH 0     /* phase 3 pulls the next node's parked rows into L2 one node ahead */
+#endif
+#ifndef NB_PIN_BASES
+#define NB_PIN_BASES 0      /* 1: list base addresses opaque (kept in registers); 2: also the tile meta / edge words / mask pointers */
+#endif
 #ifndef NB_PARK_MVC
 #define NB_PARK_MVC 1      /* 1: phase 1 parks Mvc in the APP row, phase 3 reloads it; 0: phase 3 recomputes it from the APP row + old record */
 #endif
@@ -140,35 +150,44 @@ struct TileMeta {
     __device__ __forceinline__ static int dc(const int4 &m) { return (int)((unsigned)m.x >> 24); }
 };
 
-/* a warp's private shared memory */
-template <int Q> struct WarpMem {
-    float *row[NE];          /* phase 1, per in-flight edge: clean row for the record expansion (bubble path only) */
-    uint32_t *scr[NE];       /* phase 1, per in-flight edge: selection queue (sorted keys)                          */
-    uint32_t *sel[NE];       /* phase 1: winners of the selection rounds (NB_SEL_CAPTURE = 0 / GF(16) half-warp)   */
-    float *row3[NE];         /* phase 3, per in-flight edge: clean row                                              */
-    uint32_t rowa[NE], scra[NE], sela[NE], row3a[NE];      /* the same four as shared-window addresses (hot loops)   */
+/* a warp's private shared memory.  The scratch areas are addressed from TWO per-warp bases (s1: phase 1, s3: phase 3) with
+ * compile-time offsets, so that an access is "register + immediate"; eight separately derived addresses were too many to
+ * keep in registers and ptxas rebuilt them from the kernel parameters at every use (~100 instructions per check node). */
+template <int Q, int ECN = 0> struct WarpMem {
+    static constexpr int ROWS = ECN == 0 ? NE * Q : 0;     /* floats of clean rows in front of the queues (bubble path only) */
+    uint32_t s1, s3;         /* shared-window addresses of the phase-1 scratch (clean rows | queues | winners) and the phase-3 rows */
+    unsigned char *p1, *p3;  /* the same as generic pointers (cold paths)                                    */
     uint32_t mask;           /* q = 256: ElementaryStep "seen" bits, [8][32] lane-strided (shared address)  */
     TileMeta meta;           /* [cpw] {first edge | degree << 24 (0 = skip), frame}                         */
     uint32_t *ew;            /* [cpw][dc_max] einfo words of the tile's edges (one coalesced load per tile) */
     Lists ls;
+    /* phase 1, per in-flight edge: clean row for the record expansion | selection queue (sorted keys) | winners of the rounds */
+    __device__ __forceinline__ uint32_t rowa(int e) const { return s1 + (uint32_t)(e * Q * 4); }
+    __device__ __forceinline__ uint32_t scra(int e) const { return s1 + (uint32_t)((ROWS + e * QTraits<Q>::SCR_WORDS) * 4); }
+    __device__ __forceinline__ uint32_t sela(int e) const { return s1 + (uint32_t)((ROWS + NE * QTraits<Q>::SCR_WORDS + e * 36) * 4); }
+    /* phase 3, per in-flight edge: clean row */
+    __device__ __forceinline__ uint32_t row3a(int e) const { return s3 + (uint32_t)(e * Q * 4); }
+    __device__ __forceinline__ float *row(int e) const { return reinterpret_cast<float *>(p1) + e * Q; }
+    __device__ __forceinline__ float *row3(int e) const { return reinterpret_cast<float *>(p3) + e * Q; }
+    __device__ __forceinline__ uint32_t *scr(int e) const { return reinterpret_cast<uint32_t *>(p1) + ROWS + e * QTraits<Q>::SCR_WORDS; }
     __device__ __forceinline__ WarpMem(unsigned char *smem, const KArgs &a, int warp)
     {
         unsigned char *wa = smem + a.off_wa + warp * a.wa_bytes;
         unsigned char *wb = smem + a.off_wb + warp * a.wb_bytes;
-        const int rows = a.ecn == 0 ? NE * Q : 0;          /* floats of clean rows in front of the queues */
-#pragma unroll
-        for (int e = 0; e < NE; e++) {
-            row[e] = reinterpret_cast<float *>(wb + a.wb_scr1) + e * Q;
-            scr[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + rows + e * QTraits<Q>::SCR_WORDS;
-            sel[e] = reinterpret_cast<uint32_t *>(wb + a.wb_scr1) + rows + NE * QTraits<Q>::SCR_WORDS + e * 36;
-            row3[e] = reinterpret_cast<float *>(wb + a.wb_scr3) + e * Q;
-            rowa[e] = smem_u32(row[e]); scra[e] = smem_u32(scr[e]); sela[e] = smem_u32(sel[e]); row3a[e] = smem_u32(row3[e]);
-        }
+        p1 = wb + a.wb_scr1; p3 = wb + a.wb_scr3;
+        s1 = smem_u32(p1); s3 = smem_u32(p3);
+        asm volatile("" : "+r"(s1), "+r"(s3));              /* opaque: kept in registers, not re-derived from the parameters */
         mask = smem_u32(wa + a.wa_mask);
         meta.p = reinterpret_cast<int4 *>(wa + a.wa_meta);
         ew = reinterpret_cast<uint32_t *>(wa + a.wa_einfo);
         ls.base = smem_u32(wb + a.wb_U); ls.lenb = smem_u32(wa + a.wa_len);
         ls.lstride = a.lstride; ls.n_m = a.n_m; ls.dcm = a.dc_max; ls.lr = a.L - a.dc_max; ls.r0 = a.cpw * a.dc_max;
+#if NB_PIN_BASES >= 1
+        asm volatile("" : "+r"(ls.base), "+r"(ls.lenb));
+#endif
+#if NB_PIN_BASES >= 2
+        asm volatile("" : "+r"(mask), "+l"(ew), "+l"(meta.p));
+#endif
     }
 };
 
@@ -361,6 +380,19 @@ __device__ __forceinline__ void prefetch_node(const char *app, const char *ctov,
     }
 }
 
+/* the parked rows of ONE check node back into L2 ahead of phase 3 (a good third of them has been evicted by then) */
+template <int Q>
+__device__ __forceinline__ void prefetch_rows(const char *app, const uint32_t *ew, const int4 &m, int lane)
+{
+    constexpr int LPR = (Q * 4) / 128;
+    const int dc = TileMeta::dc(m);
+    for (int i = lane; i < dc * LPR; i += 32) {
+        const uint32_t ei = ew[i / LPR];
+        const char *p = app + (uint32_t)m.y + (ei & 0xfffffu) * (uint32_t)(Q * 4) + (uint32_t)(i % LPR) * 128u;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * GF(16): a row is 16 values, so one warp carries TWO edges of a check node side by side -- edge t in
  * lanes 0-15, edge t+1 in lanes 16-31, lane & 15 = symbol / list entry -- instead of two half-empty
@@ -373,7 +405,7 @@ __device__ __forceinline__ void gf16_phase1(const WarpMem<16> &wm, const GFTab &
     const Lists &ls = wm.ls;
     const int h = lane >> 4, idx = lane & 15, hb = lane & 16;
     const RecLane rlh(n_m, idx, rs);
-    float *scr = h ? wm.row[1] : wm.row[0];
+    float *scr = h ? wm.row(1) : wm.row(0);
     const int rounds = n_m + 1 < 16 ? n_m + 1 : 16;
     for (int t = 0; t < dc; t += 2) {
         const int te = min(t + h, dc - 1);                       /* t+h >= dc: duplicate of the last edge, nothing stored */
@@ -383,7 +415,7 @@ __device__ __forceinline__ void gf16_phase1(const WarpMem<16> &wm, const GFTab &
         float *prow = app_f + (size_t)((ei & 0xfffffu) * 16u);
         float v = prow[idx];
         const RecView r = load_record(ctov_f, (uint32_t)(e0 + te), rlh);
-        if (NB_L2_PREFETCH && t + 2 < dc) prefetch_edges<16>(app_f, ctov_f, einfo, e0 + t + 2, min(2, dc - t - 2), rs, lane);
+        if (NB_PF(16) && t + 2 < dc) prefetch_edges<16>(app_f, ctov_f, einfo, e0 + t + 2, min(2, dc - t - 2), rs, lane);
         scr[idx] = r.sat;                                        /* dense CtoV row, bubble_decoder.c:262-270 */
         __syncwarp();
         if (idx < r.stp) scr[r.sym] = r.llr;
@@ -452,7 +484,7 @@ __device__ __forceinline__ void gf16_phase3(const WarpMem<16> &wm, const GFTab &
     const Lists &ls = wm.ls;
     const int h = lane >> 4, idx = lane & 15, hb = lane & 16;
     const RecLane rlh(n_m, idx, rs);
-    float *scr = h ? wm.row3[1] : wm.row3[0];
+    float *scr = h ? wm.row3(1) : wm.row3(0);
     for (int t = 0; t < dc; t += 2) {
         const int te = min(t + h, dc - 1);
         const bool valid = t + h < dc;
@@ -511,12 +543,12 @@ __device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm
     const Lists &ls = wm.ls;
     const int dcm = a.dc_max, n_m = a.n_m, rs = a.rec_stride;
 #pragma unroll
-    for (int e = 0; e < NE; e++) fill_row_s<Q>(wm.rowa[e], lane, NB_ROW_CLEAN);
+    for (int e = 0; e < NE; e++) fill_row_s<Q>(wm.rowa(e), lane, NB_ROW_CLEAN);
     __syncwarp();
     for (int c = 0; c < cnt; c++) {
         const int4 mt = wm.meta[c];
         const int dc = TileMeta::dc(mt);
-        if (NB_L2_PREFETCH && c + 1 < cnt) prefetch_node<Q>(app, ctov, wm.ew + (c + 1) * dcm, wm.meta[c + 1], rs, lane);
+        if (NB_PF(Q) && c + 1 < cnt) prefetch_node<Q>(app, ctov, wm.ew + (c + 1) * dcm, wm.meta[c + 1], rs, lane);
         const char *app_f = app + (uint32_t)mt.y;
         const uint8_t *rec0 = reinterpret_cast<const uint8_t *>(ctov) + (uint32_t)mt.z;      /* record of the node's edge 0 */
         for (int t = 0; t < dc; t += NE) {
@@ -537,13 +569,16 @@ __device__ __forceinline__ void tile_phase1(const KArgs &a, const WarpMem<Q> &wm
 #pragma unroll
             for (int e = 0; e < NE; e++) {
                 float cv[VPL];
-                expand_record<Q>(r[e], lane, wm.rowa[e], cv, minform);
+                expand_record<Q>(r[e], lane, wm.rowa(e), cv, minform);
 #pragma unroll
                 for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334 */
                 if (NB_PARK_MVC && t + e < dc) store_row_hint<Q>(prow[e], lane, v[e], pol_keep);     /* parked for phase 3 (NB_LDPC.c:448 adds this vector) */
             }
             float llr[NE]; int sym[NE];
-            select_edges<Q, NE>(v, lane, wm.scra, wm.sela, n_m, llr, sym, a.slow_counter);
+            uint32_t scra[NE], sela[NE];
+#pragma unroll
+            for (int e = 0; e < NE; e++) { scra[e] = wm.scra(e); sela[e] = wm.sela(e); }
+            select_edges<Q, NE>(v, lane, scra, sela, n_m, llr, sym, a.slow_counter);
 #pragma unroll
             for (int e = 0; e < NE; e++) {
                 if (t + e < dc) {
@@ -569,7 +604,7 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
     const Lists &ls = wm.ls;
     const int dcm = a.dc_max, n_m = a.n_m;
 #pragma unroll
-    for (int e = 0; e < NE; e++) fill_row_s<Q>(wm.row3a[e], lane, NB_ROW_CLEAN);
+    for (int e = 0; e < NE; e++) fill_row_s<Q>(wm.row3a(e), lane, NB_ROW_CLEAN);
     __syncwarp();
     for (int c = 0; c < cnt; c++) {
         const int4 mt = wm.meta[c];
@@ -578,6 +613,7 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
         uint8_t *rec0 = reinterpret_cast<uint8_t *>(ctov) + (uint32_t)mt.z;
         /* output list of edge t (id_out): t = dc-1 -> F after dc-2 steps, else B / merge number 3dc-5+t; as an index into the tile's lists */
         const int obase = dc > 2 ? ls.r0 + c * ls.lr - dc : c * dcm;
+        if (NB_P3_PREFETCH && c + 1 < cnt) prefetch_rows<Q>(app, wm.ew + (c + 1) * dcm, wm.meta[c + 1], lane);
         for (int t = 0; t < dc; t += NE) {
             float v[NE][VPL];
             uint32_t ei[NE];
@@ -595,7 +631,7 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
                     const uint32_t var = ei[e] & 0xfffffu;
                     if (!NB_PARK_MVC) {
                         float cv[VPL];
-                        expand_record<Q>(old[e], lane, wm.row3a[e], cv, minform);
+                        expand_record<Q>(old[e], lane, wm.row3a(e), cv, minform);
 #pragma unroll
                         for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);      /* NB_LDPC.c:334, same operands as phase 1 */
                     }
@@ -604,7 +640,7 @@ __device__ __forceinline__ void tile_phase3(const KArgs &a, const WarpMem<Q> &wm
                     const RecView nr = finish_list<Q, CLOSED>(ls, li, (ei[e] >> 20) & 0xff, gf, a.offset, lane);
                     store_record(rec0, (uint32_t)te, rl, nr, n_m, lane);
                     float mcv[VPL];
-                    expand_record<Q>(nr, lane, wm.row3a[e], mcv, minform);    /* :262-281 */
+                    expand_record<Q>(nr, lane, wm.row3a(e), mcv, minform);    /* :262-281 */
 #pragma unroll
                     for (int j = 0; j < VPL; j++) v[e][j] = __fadd_rn(mcv[j], v[e][j]);      /* NB_LDPC.c:448 */
                     store_row_hint<Q>(reinterpret_cast<float *>(app_f + var * (uint32_t)(Q * 4)), lane, v[e], pol_first);
@@ -628,7 +664,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
-    WarpMem<Q> wm(smem, a, warp);
+    WarpMem<Q, ECN> wm(smem, a, warp);
     GFTab gf;
     load_gf_tables(smem, a, gf);
     load_cfg_table(smem, a);
@@ -677,7 +713,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
             const int f = w / N, n = w - f * N;
             float v[VPL];
             if (a.input_kind == 0) intake_variable<Q>(a.in + ((size_t)(base + f) * N + n) * a.logq, a.den, gf.img, lane,
-                                                      reinterpret_cast<double *>(wm.scr[0]), reinterpret_cast<float *>(wm.scr[0]) + 32, v);
+                                                      reinterpret_cast<double *>(wm.scr(0)), reinterpret_cast<float *>(wm.scr(0)) + 32, v);
             else if (Q == 64 && a.input_kind == 2) intake_apsk64<Q>(a.in + ((size_t)(base + f) * N + n) * 2, a.den, a.mod, gf.img, lane, v);
             else load_row<Q>(a.in + ((size_t)(base + f) * N + n) * Q, lane, v);
             store_row<Q>(app + ((size_t)f * N + n) * Q, lane, v);
@@ -733,8 +769,8 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                             const int e0 = TileMeta::e0(mt), dc = TileMeta::dc(mt);
                             float *app_f = reinterpret_cast<float *>(reinterpret_cast<char *>(app) + (uint32_t)mt.y);
                             const uint8_t *ctov_f = ctov + (uint32_t)mt.z - (size_t)e0 * rs;
-                            if (NB_L2_PREFETCH && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
-                            if (NB_L2_PREFETCH && c + 1 < cnt) {
+                            if (NB_PF(Q) && c == 0 && dc > 0) prefetch_edges<Q>(app_f, ctov_f, a.einfo, e0, min(NE, dc), rs, lane);
+                            if (NB_PF(Q) && c + 1 < cnt) {
                                 const int4 nx = wm.meta[c + 1];
                                 if (TileMeta::dc(nx) > 0) prefetch_edges<Q>(reinterpret_cast<float *>(reinterpret_cast<char *>(app) + (uint32_t)nx.y),
                                                                             ctov + (uint32_t)nx.z - (size_t)TileMeta::e0(nx) * rs, a.einfo, TileMeta::e0(nx),
@@ -752,6 +788,7 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                         }
                     } else {
                         tile_phase1<Q, CLOSED>(a, wm, gf, cnt, reinterpret_cast<const char *>(app), reinterpret_cast<const char *>(ctov), rl, pol_stream, pol_keep, minform, lane);
+                        if (NB_P3_PREFETCH && cnt > 0) prefetch_rows<Q>(reinterpret_cast<const char *>(app), wm.ew, wm.meta[0], lane);
                         tile_elementary_steps<Q>(wm.ls, wm.meta, cnt, dcm, wm.mask, lane, a.nb_oper);
                         tile_phase3<Q, CLOSED>(a, wm, gf, cnt, reinterpret_cast<char *>(app), reinterpret_cast<char *>(ctov), dec, rl, pol_stream, minform, decide, lane);
                     }
@@ -781,7 +818,10 @@ __global__ void __launch_bounds__(ECN ? NT_SYND : NT_MAX, CTAS_PER_SM) decode_ke
                                 for (int j = 0; j < VPL; j++) v[e][j] = __fsub_rn(v[e][j], cv[j]);
                             }
                             float llr[NE]; int sym[NE];
-                            select_edges<Q, NE>(v, lane, wm.scra, wm.sela, n_m, llr, sym, a.slow_counter);
+                            uint32_t scra[NE], sela[NE];
+#pragma unroll
+            for (int e = 0; e < NE; e++) { scra[e] = wm.scra(e); sela[e] = wm.sela(e); }
+            select_edges<Q, NE>(v, lane, scra, sela, n_m, llr, sym, a.slow_counter);
 #pragma unroll
                             for (int e = 0; e < NE; e++) {
                                 if (t + e < dc && lane < n_m) {
@@ -925,13 +965,13 @@ __global__ void __launch_bounds__(NT_MAX, 1) checknode_kernel(const KArgs a, int
         if (lane < cnt) wm.meta.set(lane, e0, dc, 0u, 0u, 0u);
         __syncwarp();
         tile_elementary_steps<Q>(ls, wm.meta, cnt, dc, wm.mask, lane, a.nb_oper);
-        fill_row_s<Q>(wm.row3a[0], lane, NB_ROW_CLEAN);       /* aliases the input lists, dead after the elementary steps (degree 2: a region of its own) */
+        fill_row_s<Q>(wm.row3a(0), lane, NB_ROW_CLEAN);       /* aliases the input lists, dead after the elementary steps (degree 2: a region of its own) */
         __syncwarp();
         for (int c = 0; c < cnt; c++)
             for (int t = 0; t < dc; t++) {
                 const RecView nr = finish_list<Q, CLOSED>(ls, ls.idx(c, id_out(dc, t), dc), a.hval[e0 + t], gf, a.offset, lane);
                 float mcv[VPL];
-                expand_record<Q>(nr, lane, wm.row3a[0], mcv, a.offset >= 0.0f);
+                expand_record<Q>(nr, lane, wm.row3a(0), mcv, a.offset >= 0.0f);
                 float *dst = cllr + ((size_t)(b0 + c) * dc + t) * Q;
                 store_row<Q>(dst, lane, mcv);
                 int *gdst = cgf + ((size_t)(b0 + c) * dc + t) * Q;
