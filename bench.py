@@ -302,7 +302,8 @@ def source_id():
 def measured_traffic(wl, ecn, B, kernel_ms):
     """DRAM bytes per launch of the decode kernel from an ncu capture (profiles/traffic_<workload>_<ecn>.json, written by
     scripts/gpu_traffic.sh).  Only a capture of THIS kernel counts: same workload, check node and frames per launch, and a
-    kernel duration within 3 % of the one measured live -- otherwise the figure is stale and null is reported."""
+    kernel duration within 3 % of the one measured live, and the same kernel sources (hash of csrc/ + include/) -- otherwise the
+    figure is stale and null is reported."""
     tp = os.path.join(ROOT, "profiles", "traffic_%s_%s.json" % (wl, ecn))
     if not os.path.exists(tp):
         return None, None
@@ -314,6 +315,9 @@ def measured_traffic(wl, ecn, B, kernel_ms):
             "kernel_ms_at_capture": tj["kernel_ms"], "kernel_ms_deviation": dev}
     if dev > 0.03:
         info["rejected"] = "kernel duration differs by more than 3 % from the live measurement: capture is stale"
+        return None, info
+    if tj.get("source_id") and tj["source_id"] != info["source_id_now"]:
+        info["rejected"] = "captured from other kernel sources (hash of csrc/ + include/ differs): capture is stale"
         return None, info
     return tj.get("dram_bytes_per_launch"), info
 
