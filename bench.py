@@ -32,11 +32,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)          # the product binding (nbldpc.py); tests/ and oracle/ stay off the product arm's path
 
 # name -> (matrix, n_m, nb_oper, offset, Eb/N0, default frames per GPU per step)        
+# The default batch is a whole number of waves of the persistent grid (296 CTAs x frames per CTA group: 1 for the 64800-bit
+# GF(256) / GF(16) codes, 8 for MatDeclercq, 4 for Mat24): a partial last wave leaves SMs idle (MatDeclercq at 4096 frames =
+# 1.73 waves measured 197 Mbit/s, at 2368 or 4736 frames 226).
 WORKLOADS = {
     "AD_64800_R12_GF256": ("matrices/AD_64800_R12_GF256", 20, 25, 0.3, 2.0, 2368),
-    "Ahmed_64800_R34_GF16": ("matrices/Ahmed_64800_R34_GF16", 16, 25, 0.3, 3.0, 4096),
-    "MatDeclercq_R12_GF64": ("matrices/MatDeclercq_R12_GF64", 20, 25, 0.3, 1.2, 4096),
-    "Mat24_N480_M240": ("matrices/Mat24_N480_M240", 16, 25, 0.3, 1.5, 65536),
+    "Ahmed_64800_R34_GF16": ("matrices/Ahmed_64800_R34_GF16", 16, 25, 0.3, 3.0, 4144),
+    "MatDeclercq_R12_GF64": ("matrices/MatDeclercq_R12_GF64", 20, 25, 0.3, 1.2, 4736),
+    "Mat24_N480_M240": ("matrices/Mat24_N480_M240", 16, 25, 0.3, 1.5, 66304),
     "N96_K48_GF64": ("matrices/N96_K48_GF64", 20, 25, 0.3, 3.0, 1 << 20),
     # full-alist file shipped with the reference, which its own LoadCode cannot read: no CPU arm for it
     "KN_64800_R34_GF256": ("matrices/KN/N64800_K48600_GF256.txt", 20, 25, 0.3, 3.4, 2368),
